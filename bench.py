@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json configs[1]: MimiCodec streaming encode+decode, 256 streams x 10 s of
+synthetic 24 kHz audio per GPU (125 frames of 80 ms each, one frame of every stream per launch
+sequence), seeded synthetic weights.  Metric: codec frames/s (one frame = 1920 samples encoded to
+8 tokens and decoded back); real-time streams = frames/s / 12.5.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" = one pass over the whole batch: 125 streaming frames x 256 streams (encode + decode).
+`value` is measured with the 10 s inputs already resident in HBM; `e2e` copies every 80 ms chunk
+from pinned host memory and reads tokens + waveform back each frame.  Multi-GPU: streams shard
+across ranks with no data-path collective (weak scaling); timing = max over ranks.
+`--impl reference` times the reference's CPU implementation of the same path (the oracle port, torch
+CPU fp32 with all host threads) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+STREAMS, SECONDS = 256, 10
+FRAMES = int(SECONDS * 12.5)
+FRAME = 1920
+METRIC, UNIT = "codec_frames_per_s", "frames/s"
+WORKLOAD = f"mimi_streaming_encode_decode_B{STREAMS}x{SECONDS}s_24kHz"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self.t.join(timeout=3)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ====================================================================== CPU arm (oracle port)
+def cpu_sample(streams: int, frames: int, threads: int):
+    """The reference's CPU path (oracle restatement, torch CPU fp32): streaming encode+decode."""
+    import torch
+    from oracle import mimi_oracle as O
+    from oracle import mimi_spec as S
+    torch.set_num_threads(threads)
+    w = S.synthetic_weights(S.OFFICIAL, seed=41)
+    x = S.synthetic_audio(streams, FRAME * (frames + 1), seed=0)
+    sc = O.StreamingCodec(w, streams)
+    with torch.no_grad():
+        c = sc.encode(x[..., :FRAME])  # warm-up frame
+        sc.decode(c)
+        t0 = time.perf_counter()
+        for i in range(1, frames + 1):
+            c = sc.encode(x[..., i * FRAME:(i + 1) * FRAME])
+            sc.decode(c)
+        dt = time.perf_counter() - t0
+    return streams * frames / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    streams, frames = 8, 4
+    cpu_sample(streams, 1, threads)
+    for _ in range(max(0, args.warmup - 1)):
+        cpu_sample(streams, 1, threads)
+    t0 = time.perf_counter()
+    vals = []
+    for _ in range(args.steps):
+        v, _ = cpu_sample(streams, frames, threads)
+        vals.append(v)
+    dt = time.perf_counter() - t0
+    value = sum(vals) / len(vals)
+    sample = f"{streams} streams x {frames} frames per step (streaming, 1 warm-up frame), torch CPU fp32"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "streams_per_gpu": STREAMS, "frames_per_stream": FRAMES},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ====================================================================== GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from oracle import mimi_spec as S  # seeded synthetic weights / audio only (no compute from oracle/)
+    from rstnet_b200 import _lib, ops
+    from rstnet_b200.codec import MimiCodec
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback; use --impl reference for the CPU arm)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    m = MimiCodec(encoder_rates=[8, 6, 5, 4], codebook_size=2048, codebook_dim=256, rvq_layers=8)
+    m.load_state_dict(S.synthetic_weights(S.OFFICIAL, seed=41), strict=True)
+    m = m.to(dev).eval()
+    m.use_cuda_graphs = True
+    B = STREAMS
+    # 10 s of audio per stream: 4 distinct seeded clips tiled over the batch, plus per-rank offset
+    base = S.synthetic_audio(8, FRAME * FRAMES, seed=100 + rank)
+    host = base.repeat(B // 8, 1, 1).contiguous().pin_memory()        # [B,1,240000] pinned host
+    x_dev = host.to(dev)                                               # resident copy for `value`
+    out_wav_host = torch.empty(B, 1, FRAME, dtype=torch.float32).pin_memory()
+    out_codes_host = torch.empty(B, 8, 1, dtype=torch.int64).pin_memory()
+
+    state = {"entered": False}
+
+    def step(resident: bool):
+        """125 streaming frames for all streams: encode chunk -> decode tokens.  One streaming scope is
+        kept for the whole run (buffers + CUDA graphs are reused) and reset between passes."""
+        if state["entered"]:
+            m.reset_streaming()
+        state["entered"] = True
+        for i in range(FRAMES):
+            if resident:
+                chunk = x_dev[..., i * FRAME:(i + 1) * FRAME]
+            else:
+                chunk = host[..., i * FRAME:(i + 1) * FRAME].to(dev, non_blocking=True)
+            codes = m.encode(chunk)
+            wav = m.decode(codes)
+            if not resident:
+                out_codes_host.copy_(codes, non_blocking=True)
+                out_wav_host.copy_(wav, non_blocking=True)
+        if not resident:
+            torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(resident: bool, steps: int):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count()
+        e0.record()
+        for _ in range(steps):
+            step(resident)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, _lib.launch_count() - l0
+
+    # launches per frame (eager count; graph replays re-issue exactly these nodes)
+    m.use_cuda_graphs = False
+    m.streaming_forever(B)
+    l0 = _lib.launch_count()
+    c = m.encode(x_dev[..., :FRAME])
+    m.decode(c)
+    launches_per_frame = _lib.launch_count() - l0
+    m.use_cuda_graphs = True
+    m.streaming_forever(B)
+    state["entered"] = False
+
+    for _ in range(max(3, args.warmup)):
+        step(True)
+    with ClockSampler(local) as cs:
+        ms, _ = timed(True, args.steps)
+    clocks = cs.summary()
+    for _ in range(1):
+        step(False)
+    ms_e2e, _ = timed(False, args.steps)
+
+    frames_total = world * B * FRAMES * args.steps
+    value = frames_total / (ms / 1e3)
+    e2e_value = frames_total / (ms_e2e / 1e3)
+
+    if rank == 0:
+        roof = roofline_pass(m, x_dev, B, dev)
+        cpu_threads = os.cpu_count() or 1
+        cv, cdt = cpu_sample(8, 4, cpu_threads)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "streams_per_gpu": B, "frames_per_stream": FRAMES, "frame_samples": FRAME,
+                       "realtime_streams_per_gpu": value / world / 12.5, "cuda_graphs": True,
+                       "l2_policy": "inputs larger than L2 (246 MB audio + 320 MB weights per pass)",
+                       "parallelism": f"dp{world}"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * FRAME * FRAMES * 4,
+                    "d2h_bytes_per_step": B * FRAMES * (FRAME * 4 + 8 * 8), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches_per_frame * FRAMES * args.steps),
+            "roofline": roof,
+            "cpu_baseline": {"value": cv, "unit": UNIT, "cores": cpu_threads, "kind": "port",
+                             "sample": f"8 streams x 4 frames streaming encode+decode, torch CPU fp32 oracle port ({cdt:.1f} s)"},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def roofline_pass(m, x_dev, B, dev):
+    """Dominant kernel = gemm_rows_f32 (all convs / linears).  Per-launch CUDA-event timing of every
+    gemm_rows launch over a few eager streaming frames (same stream as the launches); achieved =
+    algorithmic FLOPs (2*M*N*K per launch) / summed launch time."""
+    import torch
+    from rstnet_b200 import ops
+    peaks = _peaks()
+    rec = []
+    orig = ops.gemm_rows
+
+    def timed_gemm(A, a_off, a_bs, a_rs, Wt, C_, c_off, c_bs, c_rs, batch, rows, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig(A, a_off, a_bs, a_rs, Wt, C_, c_off, c_bs, c_rs, batch, rows, **kw)
+        e1.record()
+        K, N = Wt.shape
+        rec.append((e0, e1, 2.0 * batch * rows * N * K))
+
+    m.use_cuda_graphs = False
+    m.streaming_forever(B)
+    c = m.encode(x_dev[..., :FRAME])
+    m.decode(c)  # untimed warm frame
+    ops.gemm_rows = timed_gemm
+    try:
+        e_all0, e_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_all0.record()
+        nframes = 3
+        for i in range(1, 1 + nframes):
+            c = m.encode(x_dev[..., i * FRAME:(i + 1) * FRAME])
+            m.decode(c)
+        e_all1.record()
+        torch.cuda.synchronize()
+    finally:
+        ops.gemm_rows = orig
+        m.use_cuda_graphs = True
+    t_ms = sum(a.elapsed_time(b) for a, b, _ in rec)
+    flops = sum(f for _, _, f in rec)
+    achieved = flops / (t_ms * 1e-3) / 1e12
+    peak = peaks["bf16_tflops_sustained"]
+    return {"bound": "tensor", "kernel": "gemm_rows_f32 (fp32 FFMA, all conv/linear launches of a frame)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": f"{peaks['source']} bf16 sustained",
+            "launches": len(rec) // nframes, "avg_launch_us": 1e3 * t_ms / max(1, len(rec)),
+            "share_of_frame_time": t_ms / e_all0.elapsed_time(e_all1),
+            "note": "fp32 CUDA-core path (RVQ index exactness); fp32 FFMA peak ~72 TFLOP/s at 1.9 GHz"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=FRAMES,
+                    help="frames per stream per step (profiling aid: ncu runs use a short pass; the default 125 is the bench)")
+    args = ap.parse_args()
+    global FRAMES, WORKLOAD
+    if args.frames != FRAMES:
+        FRAMES = args.frames
+        WORKLOAD += f"_SHORT{FRAMES}frames"
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,142 @@
+/* rstnet_b200 — C ABI of the B200 (sm_100a) kernels behind RSTnet's real-time inference hot path.
+ *
+ * The reference (yangdongchao/RSTnet) is pure Python/PyTorch and has no FFI of its own; the
+ * drop-in boundary is its Python class surface.  Each entry point below replaces
+ * the ATen call cluster of one reference method (cited as file:line under /root/reference) and is
+ * what a replacement library must export.  Conventions:
+ *   - plain C: raw DEVICE pointers, explicit sizes/strides in ELEMENTS, no torch types;
+ *   - the caller owns every buffer (activations, KV rings, conv carry rows, scratch);
+ *   - `stream` is a cudaStream_t (torch.cuda.current_stream().cuda_stream); launches are
+ *     asynchronous, never synchronise the device, and are CUDA-graph capturable;
+ *   - return 0 on success, non-zero on error with text in rstnet_last_error() (thread-local);
+ *     functions never throw and never call exit();
+ *   - no CPU fallback: without a CUDA device every compute entry point fails.
+ *
+ * Activation layout is time-major / channels-last ("NWC"): [B, T, C] fp32 with C contiguous.
+ * A causal conv over that layout is a GEMM whose A rows are OVERLAPPING windows of the input
+ * (row (b,t) = k*Cin contiguous floats starting at input row t*stride), so convs, transposed
+ * convs and linears all go through rstnet_gemm_rows_f32.
+ */
+#ifndef RSTNET_B200_H
+#define RSTNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* rstnet_stream_t; /* cudaStream_t */
+
+enum { RSTNET_ACT_NONE = 0, RSTNET_ACT_ELU = 1, RSTNET_ACT_GELU = 2 };
+
+int rstnet_version(void);
+const char* rstnet_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t rstnet_launch_count(void);
+
+/* ---- strided-row GEMM: C[b,t,:] = post( R[b,t,:] + scale * (pre(A_row(b,t)) . Wt + bias) )
+ * A_row(b,t) = K contiguous floats at A + b*a_batch_stride + t*a_row_stride.
+ * Wt is [K][N] row-major.  bias/scale/R may be NULL.  Requires K%4==0, N%4==0, 16-byte aligned
+ * rows.  Replaces: nn.Conv1d inside StreamingConv1d.forward (modules/conv.py:232-254,
+ * modules/streaming.py:216-244); nn.ConvTranspose1d inside StreamingConvTranspose1d.forward
+ * (conv.py:306-329, streaming.py:270-303; k == 2*stride rewritten as a GEMM over [x[t-1],x[t]]);
+ * F.linear in StreamingMultiheadAttention / StreamingTransformerLayer
+ * (modules/transformer.py:375-419, 550-577); the 1x1 Conv1d projections of
+ * ResidualVectorQuantizer (quantization/vq.py:80-91); ELU / GELU / LayerScale / residual adds
+ * around them (modules/seanet.py:92-94, transformer.py:559-577). */
+typedef struct {
+  const float* A;
+  int64_t a_batch_stride, a_row_stride;
+  const float* Wt;
+  const float* bias;
+  const float* scale;
+  const float* R;
+  int64_t r_batch_stride, r_row_stride;
+  float* C;
+  int64_t c_batch_stride, c_row_stride;
+  int32_t batch, rows, N, K;
+  int32_t pre_act, post_act;
+} rstnet_gemm_rows_args;
+int rstnet_gemm_rows_f32(const rstnet_gemm_rows_args* args, rstnet_stream_t stream);
+
+/* ---- first SEANet encoder conv, Cin == 1 (modules/seanet.py:177-187): x [B, xrows] (padded,
+ * xrows >= T + k - 1), w [Cout][k], out rows at out + b*out_batch_stride + t*Cout. */
+int rstnet_conv1d_cin1_f32(const float* x, int64_t x_batch_stride, const float* w, const float* bias,
+                           float* out, int64_t out_batch_stride, int32_t batch, int32_t T,
+                           int32_t Cout, int32_t k, int32_t post_act, rstnet_stream_t stream);
+
+/* ---- last SEANet decoder conv, Cout == 1 (modules/seanet.py:372-384): x [B, rows, Cin] NWC
+ * (padded, already activated), w [k*Cin] ((tap, ci) order), out [B, T]. */
+int rstnet_conv1d_cout1_f32(const float* x, int64_t x_batch_stride, const float* w, const float* bias,
+                            float* out, int64_t out_batch_stride, int32_t batch, int32_t T,
+                            int32_t Cin, int32_t k, rstnet_stream_t stream);
+
+/* ---- ConvTrUpsample1d, depthwise ConvTranspose1d k == 2*stride, no bias
+ * (modules/resample.py:86-119): x [B, 1+T, C] with one carry row in front, w [C][k],
+ * out[b, t*s+j, c] = x[t]*w[c][j] + x[t-1]*w[c][j+s]. */
+int rstnet_convtr1d_depthwise_f32(const float* x, int64_t x_batch_stride, const float* w, float* out,
+                                  int64_t out_batch_stride, int32_t batch, int32_t T, int32_t C,
+                                  int32_t stride, rstnet_stream_t stream);
+
+/* ---- row utilities for padding / streaming carry (F.pad in conv.py:81-100;
+ * `previous` / `partial` state in streaming.py:216-303).
+ * fill: rows [row0,row0+nrows) of buf[B, *, C] := 0 (mode 0) or := row `src_row` (mode 1, replicate).
+ * If `only_if_zero` is non-NULL the fill happens only when *only_if_zero == 0 (first streaming
+ * step).  copy_table: executes a device-resident table of row-block copies (all conv carries of
+ * one step in a single launch); entry layout = rstnet_row_copy. */
+int rstnet_rows_fill_f32(float* buf, int64_t batch_stride, int32_t batch, int32_t C, int32_t row0,
+                         int32_t nrows, int32_t mode, int32_t src_row, const int64_t* only_if_zero,
+                         rstnet_stream_t stream);
+typedef struct {
+  float* buf;
+  int64_t batch_stride; /* elements */
+  int32_t C, src_row, dst_row, nrows;
+} rstnet_row_copy;
+int rstnet_rows_copy_table_f32(const rstnet_row_copy* table_dev, int32_t n_entries, int32_t batch,
+                               rstnet_stream_t stream);
+/* offsets[i] += delta (device int64 counters: StreamingTransformer.offset, transformer.py:686-690) */
+int rstnet_counter_add(int64_t* counter, int64_t delta, rstnet_stream_t stream);
+
+/* ---- nn.LayerNorm over the last dim, eps inside sqrt (modules/transformer.py:113-114).
+ * x row (b,t) at x + b*x_batch_stride + t*dim; y is contiguous [batch*rows_per_batch, dim]. */
+int rstnet_layer_norm_f32(const float* x, int64_t x_batch_stride, const float* weight, const float* bias,
+                          float* y, int32_t batch, int32_t rows_per_batch, int32_t dim, float eps,
+                          rstnet_stream_t stream);
+
+/* ---- codec transformer attention (modules/transformer.py:375-419, modules/rope.py:11-68,
+ * RingKVCache transformer.py:211-278).
+ * qkv [B, T, 3*H*D] laid out (p h d).  Step 1 rotates q,k by the pair-RoPE angle of absolute
+ * position (*offset + t), writes rotated q back in place and k,v into the ring kv[2][B][H][cap][D]
+ * at slot (pos % cap).  Step 2 attends each query over keys with positions in
+ * (pos_q - context, pos_q] that are still in the ring, fp32 softmax, out [B, T, H*D].
+ * `offset` is a device int64 (positions already written before this call). */
+int rstnet_rope_kv_append_f32(float* qkv, float* kv, const int64_t* offset, const float* freqs,
+                              int32_t batch, int32_t T, int32_t H, int32_t D, int32_t cap,
+                              rstnet_stream_t stream);
+int rstnet_ring_attention_f32(const float* qkv, const float* kv, const int64_t* offset, float* out,
+                              int32_t batch, int32_t T, int32_t H, int32_t D, int32_t cap,
+                              int32_t context, rstnet_stream_t stream);
+
+/* ---- SplitResidualVectorQuantizer.encode (quantization/vq.py:305-315; core_vq.py:179-185,
+ * 365-376): x [N, ldx] holds the two projected latents (rvq_first at column 0, rvq_rest at
+ * column dim); Et [n_q][dim][bins] are the centroids TRANSPOSED, enorm [n_q][bins] their squared
+ * norms.  Distances follow torch.cdist's matmul form sqrt(max(|x|^2+|e|^2-2x.e, 0)); argmin
+ * keeps the first minimum.  codes out: int64 [B][n_q][T] with N == B*T (frame n = b*T + t).
+ * work: scratch of rstnet_rvq_encode_workspace(N, ...) bytes. */
+int64_t rstnet_rvq_encode_workspace(int64_t N, int32_t n_q, int32_t dim, int32_t bins);
+int rstnet_rvq_encode_f32(const float* x, int64_t ldx, const float* E, const float* Et,
+                          const float* enorm, int64_t* codes, void* work, int64_t N, int32_t T,
+                          int32_t n_q, int32_t n_q_semantic, int32_t dim, int32_t bins,
+                          rstnet_stream_t stream);
+/* ---- SplitResidualVectorQuantizer.decode gather part (vq.py:317-323; core_vq.py:198-206,
+ * 378-384): q [N, 2*dim] = [ E0[c0] | sum_{l>=n_q_semantic} E_l[c_l] ]; the two output_proj are
+ * then one rstnet_gemm_rows_f32 with K = 2*dim. */
+int rstnet_rvq_decode_gather_f32(const int64_t* codes, const float* E, float* q, int64_t N, int32_t T,
+                                 int32_t n_q, int32_t n_q_semantic, int32_t dim, int32_t bins,
+                                 rstnet_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSTNET_B200_H */

@@ -1,0 +1,93 @@
+"""ctypes binding of librstnet_b200.so (the C ABI declared in include/rstnet_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or an entry point fails, this module
+raises.  Build with ``python -m rstnet_b200.build`` (nvcc, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "librstnet_b200.so")
+
+ACT_NONE, ACT_ELU, ACT_GELU = 0, 1, 2
+
+# every symbol include/rstnet_b200.h declares (tests assert the .so exports all of them)
+SYMBOLS = [
+    "rstnet_version", "rstnet_last_error", "rstnet_launch_count",
+    "rstnet_gemm_rows_f32", "rstnet_conv1d_cin1_f32", "rstnet_conv1d_cout1_f32",
+    "rstnet_convtr1d_depthwise_f32", "rstnet_rows_fill_f32", "rstnet_rows_copy_table_f32",
+    "rstnet_counter_add", "rstnet_layer_norm_f32", "rstnet_rope_kv_append_f32",
+    "rstnet_ring_attention_f32", "rstnet_rvq_encode_workspace", "rstnet_rvq_encode_f32",
+    "rstnet_rvq_decode_gather_f32",
+]
+
+
+class GemmRowsArgs(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("a_batch_stride", C.c_int64), ("a_row_stride", C.c_int64),
+        ("Wt", C.c_void_p), ("bias", C.c_void_p), ("scale", C.c_void_p),
+        ("R", C.c_void_p), ("r_batch_stride", C.c_int64), ("r_row_stride", C.c_int64),
+        ("C", C.c_void_p), ("c_batch_stride", C.c_int64), ("c_row_stride", C.c_int64),
+        ("batch", C.c_int32), ("rows", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("pre_act", C.c_int32), ("post_act", C.c_int32),
+    ]
+
+
+class RowCopy(C.Structure):
+    _fields_ = [("buf", C.c_void_p), ("batch_stride", C.c_int64), ("C", C.c_int32), ("src_row", C.c_int32),
+                ("dst_row", C.c_int32), ("nrows", C.c_int32)]
+
+
+class RstnetError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the library once; fail loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RstnetError(
+            f"{LIB_PATH} not found: the CUDA extension is not built. Run `python -m rstnet_b200.build` "
+            "(there is no CPU fallback).")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    L.rstnet_version.restype = C.c_int
+    L.rstnet_last_error.restype = C.c_char_p
+    L.rstnet_launch_count.restype = i64
+    L.rstnet_gemm_rows_f32.argtypes = [C.POINTER(GemmRowsArgs), vp]
+    L.rstnet_conv1d_cin1_f32.argtypes = [vp, i64, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp]
+    L.rstnet_conv1d_cout1_f32.argtypes = [vp, i64, vp, vp, vp, i64, i32, i32, i32, i32, vp]
+    L.rstnet_convtr1d_depthwise_f32.argtypes = [vp, i64, vp, vp, i64, i32, i32, i32, i32, vp]
+    L.rstnet_rows_fill_f32.argtypes = [vp, i64, i32, i32, i32, i32, i32, i32, vp, vp]
+    L.rstnet_rows_copy_table_f32.argtypes = [vp, i32, i32, vp]
+    L.rstnet_counter_add.argtypes = [vp, i64, vp]
+    L.rstnet_layer_norm_f32.argtypes = [vp, i64, vp, vp, vp, i32, i32, i32, f32, vp]
+    L.rstnet_rope_kv_append_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    L.rstnet_ring_attention_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    L.rstnet_rvq_encode_workspace.argtypes = [i64, i32, i32, i32]
+    L.rstnet_rvq_encode_workspace.restype = i64
+    L.rstnet_rvq_encode_f32.argtypes = [vp, i64, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp]
+    L.rstnet_rvq_decode_gather_f32.argtypes = [vp, vp, vp, i64, i32, i32, i32, i32, i32, vp]
+    for name in SYMBOLS:
+        fn = getattr(L, name)
+        if fn.restype is C.c_int and name not in ("rstnet_version",):
+            pass
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().rstnet_last_error()
+        raise RstnetError(f"{what or 'rstnet call'} failed (rc={rc}): {msg.decode() if msg else '?'}")
+
+
+def launch_count() -> int:
+    return int(lib().rstnet_launch_count())

@@ -1,0 +1,150 @@
+// Codec transformer attention: pair-RoPE + ring-KV append, then masked ring attention.
+// Follows StreamingMultiheadAttention.forward (modules/transformer.py:375-419), apply_rope
+// (modules/rope.py:11-68) and RingKVCache.complete (transformer.py:211-278) of the reference.
+// HBM/L2-bound gather work (0.05 GMAC per stream-second): CUDA cores, one warp per query.
+#include "common.cuh"
+#include "../../include/rstnet_b200.h"
+
+namespace rstnet {
+extern void count_launch();
+
+// one warp per (b, t, h); lanes stride over the D/2 rotation pairs
+__global__ void rope_kv_append_kernel(float* __restrict__ qkv, float* __restrict__ kv, const long long* __restrict__ offset,
+                                      const float* __restrict__ freqs, int B, int T, int H, int D, int cap) {
+  const long long wid = (long long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  const long long total = (long long)B * T * H;
+  if (wid >= total) return;
+  const int h = (int)(wid % H);
+  const int t = (int)((wid / H) % T);
+  const int b = (int)(wid / ((long long)H * T));
+  const long long pos = *offset + t;
+  const int slot = (int)(pos % cap);
+  const int HD = H * D;
+  float* q = qkv + ((long long)(b * (long long)T + t) * 3) * HD + h * D;
+  float* k = q + HD;
+  const float* v = q + 2 * HD;
+  float* kdst = kv + (((long long)b * H + h) * cap + slot) * D;
+  float* vdst = kv + (long long)B * H * cap * D + (((long long)b * H + h) * cap + slot) * D;
+  // ts = offset.float() + arange(T) in fp32 (rope.py:39)
+  const float ts = __fadd_rn((float)(*offset), (float)t);
+  for (int pr = lane; pr < D / 2; pr += 32) {
+    const float ang = __fmul_rn(freqs[pr], ts);
+    const float c = cosf(ang), s = sinf(ang);
+    const float qr = q[2 * pr], qi = q[2 * pr + 1];
+    const float kr = k[2 * pr], ki = k[2 * pr + 1];
+    // separate mul / sub / add (no FMA contraction) as the eager reference evaluates them
+    q[2 * pr] = __fsub_rn(__fmul_rn(qr, c), __fmul_rn(qi, s));
+    q[2 * pr + 1] = __fadd_rn(__fmul_rn(qr, s), __fmul_rn(qi, c));
+    kdst[2 * pr] = __fsub_rn(__fmul_rn(kr, c), __fmul_rn(ki, s));
+    kdst[2 * pr + 1] = __fadd_rn(__fmul_rn(kr, s), __fmul_rn(ki, c));
+    vdst[2 * pr] = v[2 * pr];
+    vdst[2 * pr + 1] = v[2 * pr + 1];
+  }
+}
+
+// one warp per (b, h, tq): lane j scores key j of each 32-key block, online softmax, then the
+// lanes own output dims (lane, lane+32, ...) for the P.V accumulation (coalesced V reads).
+__global__ void ring_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ kv,
+                                      const long long* __restrict__ offset, float* __restrict__ out, int B, int T, int H,
+                                      int D, int cap, int context) {
+  extern __shared__ __align__(16) float qs_all[];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const long long wid = (long long)blockIdx.x * (blockDim.x / 32) + warp;
+  const long long total = (long long)B * T * H;
+  float* qs = qs_all + warp * D;
+  const bool active = wid < total;
+  int h = 0, t = 0, b = 0;
+  if (active) {
+    h = (int)(wid % H);
+    t = (int)((wid / H) % T);
+    b = (int)(wid / ((long long)H * T));
+    const float* q = qkv + ((long long)(b * (long long)T + t) * 3) * H * D + h * D;
+    for (int d = lane; d < D; d += 32) qs[d] = q[d];
+  }
+  __syncwarp();
+  if (!active) return;
+  const long long off = *offset;
+  const long long end = off + T;
+  const long long pos_q = off + t;
+  long long lo = pos_q - context + 1;
+  if (lo < 0) lo = 0;
+  if (lo < end - cap) lo = end - cap;
+  const float* Kb = kv + ((long long)b * H + h) * cap * D;
+  const float* Vb = Kb + (long long)B * H * cap * D;
+  const float scale = 1.0f / sqrtf((float)D);
+  float m = -INFINITY, l = 0.f;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long p0 = lo; p0 <= pos_q; p0 += 32) {
+    const long long p = p0 + lane;
+    const bool valid = p <= pos_q;
+    const int slot = (int)((valid ? p : pos_q) % cap);
+    float s = -INFINITY;
+    if (valid) {
+      const float4* kp = reinterpret_cast<const float4*>(Kb + (long long)slot * D);
+      const float4* qp = reinterpret_cast<const float4*>(qs);
+      float dot = 0.f;
+      for (int d4 = 0; d4 < D / 4; ++d4) {
+        const float4 kk = kp[d4], qq = qp[d4];
+        dot = fmaf(qq.x, kk.x, dot); dot = fmaf(qq.y, kk.y, dot);
+        dot = fmaf(qq.z, kk.z, dot); dot = fmaf(qq.w, kk.w, dot);
+      }
+      s = dot * scale;
+    }
+    const float m_new = fmaxf(m, warp_max(s));
+    const float corr = expf(m - m_new);  // exp(-inf) = 0 on the first block
+    const float pj = valid ? expf(s - m_new) : 0.f;
+    l = l * corr + warp_sum(pj);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] *= corr;
+    const int nk = (int)min(32LL, pos_q - p0 + 1);
+    for (int j = 0; j < nk; ++j) {
+      const float pw = __shfl_sync(0xffffffffu, pj, j);
+      const int sj = __shfl_sync(0xffffffffu, slot, j);
+      const float* vp = Vb + (long long)sj * D;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int d = lane + 32 * i;
+        if (d < D) acc[i] = fmaf(pw, vp[d], acc[i]);
+      }
+    }
+    m = m_new;
+  }
+  float* o = out + ((long long)b * T + t) * H * D + h * D;
+  const float inv = 1.0f / l;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int d = lane + 32 * i;
+    if (d < D) o[d] = acc[i] * inv;
+  }
+}
+
+}  // namespace rstnet
+using namespace rstnet;
+
+extern "C" int rstnet_rope_kv_append_f32(float* qkv, float* kv, const int64_t* offset, const float* freqs, int32_t batch,
+                                         int32_t T, int32_t H, int32_t D, int32_t cap, rstnet_stream_t stream) {
+  RSTNET_REQUIRE(qkv && kv && offset && freqs, "rope_kv_append: null pointer");
+  RSTNET_REQUIRE(batch > 0 && T > 0 && H > 0 && D > 0 && D % 2 == 0 && cap > 0, "rope_kv_append: bad shape");
+  RSTNET_REQUIRE(T <= cap, "rope_kv_append: T (%d) exceeds ring capacity (%d)", T, cap);
+  const long long total = (long long)batch * T * H;
+  const int warps = 8;
+  rope_kv_append_kernel<<<ceil_div(total, warps), warps * 32, 0, (cudaStream_t)stream>>>(
+      qkv, kv, (const long long*)offset, freqs, batch, T, H, D, cap);
+  count_launch();
+  return check_launch("rope_kv_append");
+}
+
+extern "C" int rstnet_ring_attention_f32(const float* qkv, const float* kv, const int64_t* offset, float* out,
+                                         int32_t batch, int32_t T, int32_t H, int32_t D, int32_t cap, int32_t context,
+                                         rstnet_stream_t stream) {
+  RSTNET_REQUIRE(qkv && kv && offset && out, "ring_attention: null pointer");
+  RSTNET_REQUIRE(batch > 0 && T > 0 && H > 0 && D > 0 && D % 4 == 0 && D <= 128 && cap > 0 && context > 0,
+                 "ring_attention: bad shape (D %% 4 == 0 and D <= 128 required)");
+  const long long total = (long long)batch * T * H;
+  const int warps = 4;
+  ring_attention_kernel<<<ceil_div(total, warps), warps * 32, warps * D * sizeof(float), (cudaStream_t)stream>>>(
+      qkv, kv, (const long long*)offset, out, batch, T, H, D, cap, context);
+  count_launch();
+  return check_launch("ring_attention");
+}

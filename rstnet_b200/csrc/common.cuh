@@ -1,0 +1,56 @@
+// Shared helpers for the rstnet_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+namespace rstnet {
+
+// thread-local last error text, exported through rstnet_last_error()
+void set_error(const char* fmt, ...);
+int  check_launch(const char* what);
+
+#define RSTNET_REQUIRE(cond, ...)                      \
+  do {                                                 \
+    if (!(cond)) {                                     \
+      ::rstnet::set_error(__VA_ARGS__);                \
+      return 1;                                        \
+    }                                                  \
+  } while (0)
+
+enum Act : int { ACT_NONE = 0, ACT_ELU = 1, ACT_GELU = 2 };
+
+// ELU(alpha=1) exactly as ATen's CPU kernel evaluates it: x <= 0 ? exp(x) - 1 : x
+// (aten/src/ATen/native/cpu/Activation.cpp elu_kernel; not expm1).
+__device__ __forceinline__ float elu_f(float x) { return x <= 0.f ? (expf(x) - 1.0f) : x; }
+// exact (erf) GELU, torch.nn.functional.gelu default
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == ACT_ELU) return elu_f(x);
+  if (act == ACT_GELU) return gelu_f(x);
+  return x;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+  uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace rstnet

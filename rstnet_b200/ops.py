@@ -1,0 +1,127 @@
+"""Thin tensor-level wrappers over the C ABI (include/rstnet_b200.h).
+
+PyTorch is plumbing here: it owns device memory and streams; all arithmetic happens in
+librstnet_b200.so.  Every wrapper takes CUDA tensors, passes raw pointers + the current stream,
+and raises on failure (no fallback path).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ACT_ELU, ACT_GELU, ACT_NONE, GemmRowsArgs, RowCopy  # noqa: F401
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.RstnetError("rstnet_b200 ops need CUDA tensors (there is no CPU path)")
+
+
+def gemm_rows(A: torch.Tensor, a_off: int, a_bs: int, a_rs: int, Wt: torch.Tensor, C_: torch.Tensor, c_off: int,
+              c_bs: int, c_rs: int, batch: int, rows: int, *, bias=None, scale=None, R=None, r_off: int = 0,
+              r_bs: int = 0, r_rs: int = 0, pre_act: int = ACT_NONE, post_act: int = ACT_NONE) -> None:
+    """C[b,t,:] = post(R + scale*(pre(A_row(b,t)) @ Wt + bias)); offsets/strides in elements."""
+    _cuda(A, Wt, C_, bias, scale, R)
+    K, N = Wt.shape
+    a = GemmRowsArgs()
+    a.A = A.data_ptr() + 4 * a_off
+    a.a_batch_stride, a.a_row_stride = a_bs, a_rs
+    a.Wt = Wt.data_ptr()
+    a.bias, a.scale = _p(bias), _p(scale)
+    a.R = None if R is None else R.data_ptr() + 4 * r_off
+    a.r_batch_stride, a.r_row_stride = r_bs, r_rs
+    a.C = C_.data_ptr() + 4 * c_off
+    a.c_batch_stride, a.c_row_stride = c_bs, c_rs
+    a.batch, a.rows, a.N, a.K = batch, rows, N, K
+    a.pre_act, a.post_act = pre_act, post_act
+    _lib.check(_lib.lib().rstnet_gemm_rows_f32(C.byref(a), _stream()), "gemm_rows_f32")
+
+
+def conv1d_cin1(x, x_bs, w, bias, out, out_off, out_bs, batch, T, Cout, k, post_act=ACT_NONE):
+    _cuda(x, w, out)
+    _lib.check(_lib.lib().rstnet_conv1d_cin1_f32(x.data_ptr(), x_bs, w.data_ptr(), _p(bias), out.data_ptr() + 4 * out_off,
+                                                 out_bs, batch, T, Cout, k, post_act, _stream()), "conv1d_cin1")
+
+
+def conv1d_cout1(x, x_bs, w, bias, out, out_bs, batch, T, Cin, k):
+    _cuda(x, w, out)
+    _lib.check(_lib.lib().rstnet_conv1d_cout1_f32(x.data_ptr(), x_bs, w.data_ptr(), _p(bias), out.data_ptr(), out_bs,
+                                                  batch, T, Cin, k, _stream()), "conv1d_cout1")
+
+
+def convtr1d_depthwise(x, x_bs, w, out, out_off, out_bs, batch, T, Cch, stride):
+    _cuda(x, w, out)
+    _lib.check(_lib.lib().rstnet_convtr1d_depthwise_f32(x.data_ptr(), x_bs, w.data_ptr(), out.data_ptr() + 4 * out_off,
+                                                        out_bs, batch, T, Cch, stride, _stream()), "convtr1d_depthwise")
+
+
+def rows_fill(buf, bs, batch, Cch, row0, nrows, mode=0, src_row=0, only_if_zero=None):
+    _cuda(buf)
+    _lib.check(_lib.lib().rstnet_rows_fill_f32(buf.data_ptr(), bs, batch, Cch, row0, nrows, mode, src_row,
+                                               _p(only_if_zero), _stream()), "rows_fill")
+
+
+def rows_copy_table(table_dev: torch.Tensor, n_entries: int, batch: int):
+    _lib.check(_lib.lib().rstnet_rows_copy_table_f32(table_dev.data_ptr(), n_entries, batch, _stream()), "rows_copy_table")
+
+
+def make_copy_table(entries, device) -> torch.Tensor:
+    """entries: list of (tensor, batch_stride, C, src_row, dst_row, nrows) -> device uint8 tensor."""
+    arr = (RowCopy * len(entries))()
+    for i, (t, bs, c, s, d, n) in enumerate(entries):
+        if n > 0 and not (s >= d):
+            raise _lib.RstnetError("carry copy must move rows towards the front (src_row >= dst_row)")
+        arr[i].buf, arr[i].batch_stride, arr[i].C, arr[i].src_row, arr[i].dst_row, arr[i].nrows = t.data_ptr(), bs, c, s, d, n
+    raw = bytes(arr)
+    return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+
+
+def counter_add(counter: torch.Tensor, delta: int):
+    _lib.check(_lib.lib().rstnet_counter_add(counter.data_ptr(), delta, _stream()), "counter_add")
+
+
+def layer_norm(x, x_off, x_bs, w, b, y, batch, rows, dim, eps):
+    _cuda(x, w, b, y)
+    _lib.check(_lib.lib().rstnet_layer_norm_f32(x.data_ptr() + 4 * x_off, x_bs, w.data_ptr(), b.data_ptr(), y.data_ptr(),
+                                                batch, rows, dim, eps, _stream()), "layer_norm")
+
+
+def rope_kv_append(qkv, kv, offset, freqs, batch, T, H, D, cap):
+    _cuda(qkv, kv, offset, freqs)
+    _lib.check(_lib.lib().rstnet_rope_kv_append_f32(qkv.data_ptr(), kv.data_ptr(), offset.data_ptr(), freqs.data_ptr(),
+                                                    batch, T, H, D, cap, _stream()), "rope_kv_append")
+
+
+def ring_attention(qkv, kv, offset, out, batch, T, H, D, cap, context):
+    _cuda(qkv, kv, offset, out)
+    _lib.check(_lib.lib().rstnet_ring_attention_f32(qkv.data_ptr(), kv.data_ptr(), offset.data_ptr(), out.data_ptr(),
+                                                    batch, T, H, D, cap, context, _stream()), "ring_attention")
+
+
+def rvq_encode_workspace(N, n_q, dim, bins) -> int:
+    return int(_lib.lib().rstnet_rvq_encode_workspace(N, n_q, dim, bins))
+
+
+def rvq_encode(x, ldx, E, Et, enorm, codes, work, N, T, n_q, ns, dim, bins):
+    _cuda(x, E, Et, enorm, codes, work)
+    _lib.check(_lib.lib().rstnet_rvq_encode_f32(x.data_ptr(), ldx, E.data_ptr(), Et.data_ptr(), enorm.data_ptr(),
+                                                codes.data_ptr(), work.data_ptr(), N, T, n_q, ns, dim, bins, _stream()),
+               "rvq_encode")
+
+
+def rvq_decode_gather(codes, E, q, N, T, n_q, ns, dim, bins):
+    _cuda(codes, E, q)
+    _lib.check(_lib.lib().rstnet_rvq_decode_gather_f32(codes.data_ptr(), E.data_ptr(), q.data_ptr(), N, T, n_q, ns, dim,
+                                                       bins, _stream()), "rvq_decode_gather")

@@ -1,0 +1,348 @@
+"""GPU parity tests (-m gpu): every CUDA kernel of the codec path against the CPU oracle on the
+same seeded inputs, the whole codec against the golden vectors of the unmodified reference, and
+the reference's own properties (streaming == batch, causality) on the CUDA path.
+
+Tolerances (fp32 everywhere on this path): activations/waveforms max-abs 2e-4 relative to a
+signal of O(1) (different fp32 summation order only); RVQ indices bit-exact wherever the
+float64 top-1/top-2 margin exceeds 1e-4, and bit-exact in isolation on oracle latents.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import mimi_oracle as O
+from oracle import mimi_spec as S
+
+pytestmark = pytest.mark.gpu
+
+from rstnet_b200 import ops
+from rstnet_b200._lib import ACT_ELU, ACT_GELU, ACT_NONE
+from rstnet_b200.codec import MimiCodec
+
+DEV = "cuda"
+
+
+def _maxdiff(a, b):
+    return (a.float().cpu() - b.float().cpu()).abs().max().item()
+
+
+@pytest.fixture(scope="module")
+def codec(official_weights):
+    m = MimiCodec(encoder_rates=[8, 6, 5, 4], codebook_size=2048, codebook_dim=256, rvq_layers=8)
+    m.load_state_dict(official_weights, strict=True)
+    return m.to(DEV).eval()
+
+
+# ------------------------------------------------------------------ kernels in isolation
+@pytest.mark.parametrize("B,Cin,Cout,k,s,T", [
+    (2, 64, 32, 3, 1, 100), (3, 32, 64, 1, 1, 77), (2, 64, 128, 8, 4, 480), (1, 128, 256, 10, 5, 95),
+    (2, 256, 512, 12, 6, 36), (2, 512, 1024, 16, 8, 16), (5, 1024, 512, 3, 1, 2), (2, 512, 512, 4, 2, 9),
+    (1, 512, 1024, 7, 1, 25), (300, 64, 128, 8, 4, 8),
+])
+@pytest.mark.parametrize("pre,post", [(ACT_NONE, ACT_NONE), (ACT_ELU, ACT_ELU)])
+def test_conv_as_gemm_rows(B, Cin, Cout, k, s, T, pre, post):
+    """StreamingConv1d (conv.py:232-254) as a strided-row GEMM, with fused ELU pre/post."""
+    g = torch.Generator().manual_seed(B * 1000 + Cin + k)
+    x = torch.randn(B, Cin, T, generator=g)
+    w = torch.randn(Cout, Cin, k, generator=g) / (Cin * k) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    xin = F.elu(x) if pre else x
+    ref = O.causal_conv1d(xin, w, b, stride=s)
+    if post:
+        ref = F.elu(ref)
+    Tout = ref.shape[-1]
+    ctx = k - s
+    buf = torch.zeros(B, ctx + Tout * s, Cin, device=DEV)
+    buf[:, ctx:ctx + T] = x.permute(0, 2, 1).to(DEV)
+    Wt = w.permute(2, 1, 0).reshape(k * Cin, Cout).contiguous().to(DEV)
+    out = torch.empty(B, Tout, Cout, device=DEV)
+    ops.gemm_rows(buf, 0, buf.shape[1] * Cin, s * Cin, Wt, out, 0, Tout * Cout, Cout, B, Tout, bias=b.to(DEV),
+                  pre_act=pre, post_act=post)
+    torch.cuda.synchronize()
+    assert _maxdiff(out.permute(0, 2, 1), ref) <= 2e-5 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("B,Cin,Cout,s,T", [(2, 1024, 512, 8, 4), (1, 512, 256, 6, 17), (3, 256, 128, 5, 40), (2, 128, 64, 4, 33)])
+def test_convtr_as_gemm_rows(B, Cin, Cout, s, T):
+    """StreamingConvTranspose1d k=2*stride (conv.py:306-329) as a GEMM over [x[t-1], x[t]]."""
+    g = torch.Generator().manual_seed(Cin + s)
+    x = torch.randn(B, Cin, T, generator=g)
+    w = torch.randn(Cin, Cout, 2 * s, generator=g) / (2 * Cin) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    ref = O.causal_convtr1d(x, w, b, stride=s)
+    buf = torch.zeros(B, 1 + T, Cin, device=DEV)
+    buf[:, 1:] = x.permute(0, 2, 1).to(DEV)
+    w_prev = w[:, :, s:].permute(0, 2, 1).reshape(Cin, s * Cout)
+    w_cur = w[:, :, :s].permute(0, 2, 1).reshape(Cin, s * Cout)
+    Wt = torch.cat([w_prev, w_cur], 0).contiguous().to(DEV)
+    out = torch.empty(B, T * s, Cout, device=DEV)
+    ops.gemm_rows(buf, 0, (1 + T) * Cin, Cin, Wt, out, 0, T * s * Cout, s * Cout, B, T, bias=b.repeat(s).to(DEV))
+    torch.cuda.synchronize()
+    assert ref.shape[-1] == T * s
+    assert _maxdiff(out.permute(0, 2, 1), ref) <= 2e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_gemm_rows_residual_scale_gelu_inplace():
+    """linear + LayerScale + residual written in place (transformer.py:559-577) and GELU epilogue."""
+    g = torch.Generator().manual_seed(5)
+    M, K, N = 130, 512, 2048
+    a = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    ref = F.gelu(F.linear(a, w))
+    out = torch.empty(M, N, device=DEV)
+    ops.gemm_rows(a.to(DEV), 0, M * K, K, w.t().contiguous().to(DEV), out, 0, M * N, N, 1, M, post_act=ACT_GELU)
+    assert _maxdiff(out, ref) <= 2e-5
+    x = torch.randn(M, K, generator=g)
+    w2 = torch.randn(K, N, generator=g) / N ** 0.5
+    sc = torch.rand(K, generator=g)
+    ref2 = x + sc * F.linear(ref, w2)
+    xd = x.to(DEV).clone()
+    ops.gemm_rows(out, 0, M * N, N, w2.t().contiguous().to(DEV), xd, 0, M * K, K, 1, M, scale=sc.to(DEV), R=xd, r_off=0,
+                  r_bs=M * K, r_rs=K)
+    assert _maxdiff(xd, ref2) <= 5e-5
+
+
+def test_conv_cin1_cout1_depthwise():
+    g = torch.Generator().manual_seed(9)
+    B, T = 3, 1000
+    x = torch.randn(B, 1, T, generator=g)
+    w = torch.randn(64, 1, 7, generator=g)
+    b = torch.randn(64, generator=g)
+    ref = O.causal_conv1d(x, w, b)
+    xin = torch.zeros(B, 6 + T, device=DEV)
+    xin[:, 6:] = x[:, 0].to(DEV)
+    out = torch.empty(B, T, 64, device=DEV)
+    ops.conv1d_cin1(xin, 6 + T, w.reshape(64, 7).contiguous().to(DEV), b.to(DEV), out, 0, T * 64, B, T, 64, 7)
+    assert _maxdiff(out.permute(0, 2, 1), ref) <= 1e-5
+    # Cout == 1, k3
+    x2 = torch.randn(B, 64, T, generator=g)
+    w2 = torch.randn(1, 64, 3, generator=g) / 14
+    b2 = torch.randn(1, generator=g)
+    ref2 = O.causal_conv1d(x2, w2, b2)
+    buf = torch.zeros(B, 2 + T, 64, device=DEV)
+    buf[:, 2:] = x2.permute(0, 2, 1).to(DEV)
+    out2 = torch.empty(B, T, device=DEV)
+    ops.conv1d_cout1(buf, (2 + T) * 64, w2[0].t().contiguous().reshape(-1).to(DEV), b2.to(DEV), out2, T, B, T, 64, 3)
+    assert _maxdiff(out2, ref2[:, 0]) <= 1e-5
+    # depthwise transposed conv k4 s2
+    x3 = torch.randn(B, 512, 50, generator=g)
+    w3 = torch.randn(512, 1, 4, generator=g)
+    ref3 = O.causal_convtr1d(x3, w3, None, stride=2, groups=512)
+    buf3 = torch.zeros(B, 51, 512, device=DEV)
+    buf3[:, 1:] = x3.permute(0, 2, 1).to(DEV)
+    out3 = torch.empty(B, 100, 512, device=DEV)
+    ops.convtr1d_depthwise(buf3, 51 * 512, w3.reshape(512, 4).contiguous().to(DEV), out3, 0, 100 * 512, B, 50, 512, 2)
+    assert _maxdiff(out3.permute(0, 2, 1), ref3) <= 1e-5
+
+
+def test_layer_norm():
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(3, 7, 512, generator=g) * 3 + 1
+    w, b = torch.randn(512, generator=g), torch.randn(512, generator=g)
+    ref = F.layer_norm(x, (512,), w, b, 1e-5)
+    y = torch.empty(21, 512, device=DEV)
+    ops.layer_norm(x.to(DEV), 0, 7 * 512, w.to(DEV), b.to(DEV), y, 3, 7, 512, 1e-5)
+    assert _maxdiff(y.view(3, 7, 512), ref) <= 1e-5
+
+
+@pytest.mark.parametrize("T,steps,cap,context", [(40, 1, 40, 250), (300, 1, 300, 250), (2, 140, 250, 250), (3, 9, 10, 10)])
+def test_rope_ring_attention_vs_oracle(T, steps, cap, context):
+    """StreamingMultiheadAttention core (transformer.py:375-419): pair-RoPE, ring KV, context mask."""
+    B, H, D = 2, 8, 64
+    import math
+    cfg = S.MimiConfig(context=context)
+    g = torch.Generator().manual_seed(T + steps)
+    ds = torch.arange(D // 2, dtype=torch.float32)
+    freqs = torch.exp(ds * (-math.log(10000.0) * 2 / D)).to(DEV)
+    kv = torch.zeros(2, B, H, cap, D, device=DEV)
+    offset = torch.zeros(1, dtype=torch.int64, device=DEV)
+    ring = O.KVRing(B, H, D, cap) if steps > 1 else None
+    off = 0
+    for step in range(steps):
+        qkv = torch.randn(B, T, 3 * H * D, generator=g)
+        q, k, v = qkv.view(B, T, 3, H, D).permute(2, 0, 3, 1, 4)
+        q, k = O.rope_pairs(q, k, off, 10000.0)
+        if ring is None:
+            kk, vv, pos_k = k, v, torch.arange(T)
+        else:
+            kk, vv, pos_k = ring.complete(k, v)
+        pos_q = off + torch.arange(T).view(-1, 1)
+        delta = pos_q - pos_k.view(1, -1)
+        bias = (pos_k.view(1, -1) >= 0) & (delta >= 0) & (delta < cfg.context)
+        ref = F.scaled_dot_product_attention(q, kk, vv, bias).permute(0, 2, 1, 3).reshape(B, T, H * D)
+        qd = qkv.to(DEV).contiguous()
+        out = torch.empty(B, T, H * D, device=DEV)
+        ops.rope_kv_append(qd, kv, offset, freqs, B, T, H, D, cap)
+        ops.ring_attention(qd, kv, offset, out, B, T, H, D, cap, context)
+        ops.counter_add(offset, T)
+        off += T
+        if step in (0, steps // 2, steps - 1):
+            assert _maxdiff(out, ref) <= 2e-5, step
+    assert int(offset.item()) == off
+
+
+def _run_rvq(lat_btd, w, cfg=S.OFFICIAL):
+    """lat [B,T,512] on device -> codes via proj GEMM + rvq kernels, using oracle-side packing."""
+    B, T, D = lat_btd.shape
+    cd = cfg.codebook_dim
+    E = O.codebooks(w, cfg)
+    w1 = w["quantizer.rvq_first.input_proj.weight"].reshape(cd, D)
+    w2 = w["quantizer.rvq_rest.input_proj.weight"].reshape(cd, D)
+    qin = torch.cat([w1.t(), w2.t()], 1).contiguous().to(DEV)
+    xproj = torch.empty(B * T, 2 * cd, device=DEV)
+    ops.gemm_rows(lat_btd.contiguous(), 0, T * D, D, qin, xproj, 0, T * 2 * cd, 2 * cd, B, T)
+    codes = torch.zeros(B, cfg.n_q, T, dtype=torch.int64, device=DEV)
+    work = torch.empty(ops.rvq_encode_workspace(B * T, cfg.n_q, cd, cfg.codebook_size), dtype=torch.uint8, device=DEV)
+    ops.rvq_encode(xproj, 2 * cd, E.to(DEV), E.transpose(1, 2).contiguous().to(DEV), E.pow(2).sum(-1).to(DEV), codes, work,
+                   B * T, T, cfg.n_q, cfg.n_q_semantic, cd, cfg.codebook_size)
+    torch.cuda.synchronize()
+    return codes.cpu()
+
+
+def test_rvq_encode_isolated_bit_exact_on_golden_latents(golden_dir, official_weights):
+    """RVQ search on the reference's own latents: indices must be bit-identical (SURVEY.md H1 iii)."""
+    g = np.load(os.path.join(golden_dir, "mimi_cfg1.npz"))
+    lat = torch.from_numpy(g["z_lat"])                        # [1,512,13]
+    codes = _run_rvq(lat.permute(0, 2, 1).to(DEV), official_weights)
+    assert np.array_equal(codes.numpy(), g["codes"])
+
+
+def test_rvq_encode_random_latents_and_ties(official_weights):
+    """Larger N (ragged vs the 32-frame tile), indices vs the oracle; exact centroid hits; duplicates."""
+    w = dict(official_weights)
+    g = torch.Generator().manual_seed(11)
+    z = torch.randn(3, 512, 45, generator=g) * 1.2
+    ref = O.rvq_encode(z, w)
+    margins = O.rvq_margins(z, w).min(dim=0).values            # per frame
+    got = _run_rvq(z.permute(0, 2, 1).to(DEV), w)
+    bad = (got != ref).any(dim=1).reshape(-1)
+    # frames may only differ where a float64 near-tie (< 1e-5 relative) exists
+    assert not bool((bad & (margins > 1e-5)).any()), f"mismatch on well-separated frames: {int(bad.sum())}"
+    assert bad.float().mean().item() <= 0.05
+    # duplicate centroid -> first index wins (core_vq.py:183 argmin)
+    p = "quantizer.rvq_first.vq.layers.0._codebook"
+    w[f"{p}.embedding_sum"] = w[f"{p}.embedding_sum"].clone()
+    w[f"{p}.cluster_usage"] = w[f"{p}.cluster_usage"].clone()
+    w[f"{p}.embedding_sum"][1500] = w[f"{p}.embedding_sum"][7]
+    w[f"{p}.cluster_usage"][1500] = w[f"{p}.cluster_usage"][7]
+    got2 = _run_rvq(z.permute(0, 2, 1).to(DEV), w)
+    assert not bool((got2[:, 0] == 1500).any())
+    ref2 = O.rvq_encode(z, w)
+    ok = margins.reshape(3, 45) > 1e-5
+    assert torch.equal(got2[:, 0][ok], ref2[:, 0][ok])
+
+
+def test_rvq_decode_gather(official_weights):
+    g = torch.Generator().manual_seed(4)
+    codes = torch.randint(0, 2048, (3, 8, 11), generator=g)
+    E = O.codebooks(official_weights)
+    q = torch.empty(33, 512, device=DEV)
+    ops.rvq_decode_gather(codes.to(DEV), E.to(DEV), q, 33, 11, 8, 1, 256, 2048)
+    q1 = F.embedding(codes[:, 0], E[0])
+    q2 = sum(F.embedding(codes[:, l], E[l]) for l in range(1, 8))
+    ref = torch.cat([q1, q2], -1).reshape(33, 512)
+    assert _maxdiff(q, ref) <= 1e-6
+
+
+# ------------------------------------------------------------------ whole codec vs the reference's golden vectors
+def test_cfg1_encode_decode_vs_reference_golden(golden_dir, codec):
+    g = np.load(os.path.join(golden_dir, "mimi_cfg1.npz"))
+    x = S.synthetic_audio(1, 24000, seed=int(g["audio_seed"])).to(DEV)
+    codes = codec.encode(x)
+    plan = codec._engine.enc_plan(1, 24000, False)
+    lat = plan.lat.view(1, 13, 512).permute(0, 2, 1)
+    d_lat = _maxdiff(lat, torch.from_numpy(g["z_lat"]))
+    print(f"latent max|d| vs reference = {d_lat:.3e}")
+    assert d_lat <= 2e-4
+    assert codes.shape == (1, 8, 13) and codes.dtype == torch.int64
+    margins = torch.from_numpy(g["margins"]).min(dim=0).values
+    bad = (codes.cpu() != torch.from_numpy(g["codes"])).any(dim=1).reshape(-1)
+    print(f"frames with index mismatch: {int(bad.sum())}/13; min margin {margins.min().item():.2e}")
+    assert not bool((bad & (margins > 1e-4)).any())
+    wav = codec.decode(torch.from_numpy(g["codes"]).to(DEV))
+    assert wav.shape == (1, 1, 24960)
+    d_wav = _maxdiff(wav, torch.from_numpy(g["wav"]))
+    print(f"wav max|d| vs reference = {d_wav:.3e} (peak {np.abs(g['wav']).max():.3f})")
+    assert d_wav <= 1e-4 * max(1.0, float(np.abs(g["wav"]).max()))
+    if not bool(bad.any()):
+        assert torch.equal(codes.cpu(), torch.from_numpy(g["codes"]))     # bit-exact round trip tokens
+
+
+@pytest.mark.parametrize("L", [1, 1920, 4000])
+def test_ragged_lengths_vs_reference_golden(golden_dir, codec, L):
+    g = np.load(os.path.join(golden_dir, f"mimi_len{L}.npz"))
+    x = S.synthetic_audio(2, L, seed=int(g["audio_seed"])).to(DEV)
+    codes = codec.encode(x)
+    assert codes.shape == g["codes"].shape
+    margins = O.rvq_margins(torch.from_numpy(g["z_lat"]), S.synthetic_weights()).min(dim=0).values
+    bad = (codes.cpu() != torch.from_numpy(g["codes"])).any(dim=1).reshape(-1)
+    assert not bool((bad & (margins > 1e-4)).any())
+    wav = codec.decode(torch.from_numpy(g["codes"]).to(DEV))
+    assert _maxdiff(wav, torch.from_numpy(g["wav"])) <= 1e-4 * max(1.0, float(np.abs(g["wav"]).max()))
+
+
+def test_empty_input(codec):
+    assert codec.encode(torch.zeros(2, 1, 0, device=DEV)).shape == (2, 8, 0)
+    assert codec.decode(torch.zeros(2, 8, 0, dtype=torch.int64, device=DEV)).shape == (2, 1, 0)
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_streaming_vs_reference_golden_and_batch(golden_dir, codec, graphs):
+    """MimiModel streaming (compression.py:368-423) golden + the reference property streaming == batch."""
+    g = np.load(os.path.join(golden_dir, "mimi_stream6.npz"))
+    x = S.synthetic_audio(2, 1920 * 6, seed=int(g["audio_seed"])).to(DEV)
+    codec.use_cuda_graphs = graphs
+    cs, ws = [], []
+    with codec.streaming(2):
+        for i in range(6):
+            c = codec.encode(x[..., i * 1920:(i + 1) * 1920])
+            assert c.shape == (2, 8, 1)
+            cs.append(c)
+            ws.append(codec.decode(torch.from_numpy(g["codes"][..., i:i + 1]).to(DEV)))
+    codes, wav = torch.cat(cs, -1), torch.cat(ws, -1)
+    b_codes = codec.encode(x)
+    b_wav = codec.decode(torch.from_numpy(g["codes"]).to(DEV))
+    # our streaming and batch paths run the same kernels row for row: identical results
+    assert torch.equal(codes, b_codes)
+    assert _maxdiff(wav, b_wav) == 0.0
+    assert _maxdiff(wav, torch.from_numpy(g["wav"])) <= 1e-4 * max(1.0, float(np.abs(g["wav"]).max()))
+    bad = (codes.cpu() != torch.from_numpy(g["codes"])).any(dim=1)
+    print(f"streaming frames with index mismatch vs reference: {int(bad.sum())}/12")
+    assert bad.float().mean().item() <= 0.1
+
+
+def test_streaming_reset_and_causality(codec):
+    """reset_streaming (streaming.py:115-126) restarts the stream; outputs never depend on the future."""
+    x = S.synthetic_audio(3, 1920 * 3, seed=21).to(DEV)
+    codec.use_cuda_graphs = True
+    with codec.streaming(3):
+        first = [codec.encode(x[..., i * 1920:(i + 1) * 1920]) for i in range(3)]
+        codec.reset_streaming()
+        again = [codec.encode(x[..., i * 1920:(i + 1) * 1920]) for i in range(3)]
+    for a, b in zip(first, again):
+        assert torch.equal(a, b)
+    full = codec.encode(x)
+    prefix = codec.encode(x[..., :1920 * 2])
+    assert torch.equal(full[..., :2], prefix)
+
+
+def test_cfg2_shape_properties_full_batch(codec):
+    """BASELINE configs[1] size (B=256 streams): encode -> decode -> shapes, finiteness, determinism."""
+    B = 256
+    x = S.synthetic_audio(4, 1920 * 2, seed=33).repeat(B // 4, 1, 1).to(DEV)
+    codec.use_cuda_graphs = True
+    with codec.streaming(B):
+        outs = []
+        for i in range(2):
+            c = codec.encode(x[..., i * 1920:(i + 1) * 1920])
+            outs.append((c, codec.decode(c)))
+    codes = torch.cat([o[0] for o in outs], -1)
+    wav = torch.cat([o[1] for o in outs], -1)
+    assert codes.shape == (B, 8, 2) and wav.shape == (B, 1, 3840)
+    assert torch.isfinite(wav).all() and int(codes.min()) >= 0 and int(codes.max()) < 2048
+    # identical streams give identical tokens (batch rows are independent)
+    assert torch.equal(codes[:4], codes[4:8]) and torch.equal(wav[:4], wav[252:256])
+    assert torch.equal(codes[:4], codec.encode(x[:4]))
