@@ -110,13 +110,16 @@ int rstnet_layer_norm_f32(const float* x, int64_t x_batch_stride, const float* w
  * position (*offset + t), writes rotated q back in place and k,v into the ring kv[2][B][H][cap][D]
  * at slot (pos % cap).  Step 2 attends each query over keys with positions in
  * (pos_q - context, pos_q] that are still in the ring, fp32 softmax, out [B, T, H*D].
- * `offset` is a device int64 (positions already written before this call). */
+ * `offset` is a device int64 (positions already written before this call).  linear != 0: kv is a
+ * plain [0, cap) buffer holding every position (non-streaming, KVCacheResult.from_kv); linear == 0:
+ * ring semantics of RingKVCache.complete, including its quirk that the oldest slot (position
+ * end - cap) is labelled `end_offset` and therefore masked once the ring has wrapped. */
 int rstnet_rope_kv_append_f32(float* qkv, float* kv, const int64_t* offset, const float* freqs,
                               int32_t batch, int32_t T, int32_t H, int32_t D, int32_t cap,
                               rstnet_stream_t stream);
 int rstnet_ring_attention_f32(const float* qkv, const float* kv, const int64_t* offset, float* out,
                               int32_t batch, int32_t T, int32_t H, int32_t D, int32_t cap,
-                              int32_t context, rstnet_stream_t stream);
+                              int32_t context, int32_t linear, rstnet_stream_t stream);
 
 /* ---- SplitResidualVectorQuantizer.encode (quantization/vq.py:305-315; core_vq.py:179-185,
  * 365-376): x [N, ldx] holds the two projected latents (rvq_first at column 0, rvq_rest at

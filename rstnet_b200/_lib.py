@@ -70,7 +70,7 @@ def lib() -> C.CDLL:
     L.rstnet_counter_add.argtypes = [vp, i64, vp]
     L.rstnet_layer_norm_f32.argtypes = [vp, i64, vp, vp, vp, i32, i32, i32, f32, vp]
     L.rstnet_rope_kv_append_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
-    L.rstnet_ring_attention_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    L.rstnet_ring_attention_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
     L.rstnet_rvq_encode_workspace.argtypes = [i64, i32, i32, i32]
     L.rstnet_rvq_encode_workspace.restype = i64
     L.rstnet_rvq_encode_f32.argtypes = [vp, i64, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp]

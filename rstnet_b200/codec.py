@@ -386,7 +386,7 @@ class _Engine:
             ops.layer_norm(X.t, xo, X.bs, w["n1w"], w["n1b"], ln, B, F, D, 1e-5)
             ops.gemm_rows(ln, 0, F * D, D, w["in_w"], qkv, 0, F * 3 * D, 3 * D, B, F)
             ops.rope_kv_append(qkv, kvl, offset, self.freqs, B, F, H, hd, cap)
-            ops.ring_attention(qkv, kvl, offset, att, B, F, H, hd, cap, m.context)
+            ops.ring_attention(qkv, kvl, offset, att, B, F, H, hd, cap, m.context, len(kv) == 1)
             ops.gemm_rows(att, 0, F * D, D, w["out_w"], X.t, xo, X.bs, D, B, F, scale=w["ls1"], R=X.t, r_off=xo,
                           r_bs=X.bs, r_rs=D)
             ops.layer_norm(X.t, xo, X.bs, w["n2w"], w["n2b"], ln, B, F, D, 1e-5)

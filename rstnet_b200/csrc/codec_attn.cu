@@ -47,7 +47,7 @@ __global__ void rope_kv_append_kernel(float* __restrict__ qkv, float* __restrict
 // lanes own output dims (lane, lane+32, ...) for the P.V accumulation (coalesced V reads).
 __global__ void ring_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ kv,
                                       const long long* __restrict__ offset, float* __restrict__ out, int B, int T, int H,
-                                      int D, int cap, int context) {
+                                      int D, int cap, int context, int linear) {
   extern __shared__ __align__(16) float qs_all[];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const long long wid = (long long)blockIdx.x * (blockDim.x / 32) + warp;
@@ -69,7 +69,11 @@ __global__ void ring_attention_kernel(const float* __restrict__ qkv, const float
   const long long pos_q = off + t;
   long long lo = pos_q - context + 1;
   if (lo < 0) lo = 0;
-  if (lo < end - cap) lo = end - cap;
+  // RingKVCache.complete (transformer.py:258-263) labels the slot at end_offset % capacity with
+  // position `end_offset` (its `delta <= 0` branch), so once the ring has wrapped the oldest entry
+  // (position end - cap) is masked out by `delta >= 0`: only cap - 1 keys are attendable.
+  // A linear (non-streaming, KVCacheResult.from_kv) buffer keeps every position.
+  if (!linear && lo < end - cap + 1) lo = end - cap + 1;
   const float* Kb = kv + ((long long)b * H + h) * cap * D;
   const float* Vb = Kb + (long long)B * H * cap * D;
   const float scale = 1.0f / sqrtf((float)D);
@@ -137,14 +141,14 @@ extern "C" int rstnet_rope_kv_append_f32(float* qkv, float* kv, const int64_t* o
 
 extern "C" int rstnet_ring_attention_f32(const float* qkv, const float* kv, const int64_t* offset, float* out,
                                          int32_t batch, int32_t T, int32_t H, int32_t D, int32_t cap, int32_t context,
-                                         rstnet_stream_t stream) {
+                                         int32_t linear, rstnet_stream_t stream) {
   RSTNET_REQUIRE(qkv && kv && offset && out, "ring_attention: null pointer");
   RSTNET_REQUIRE(batch > 0 && T > 0 && H > 0 && D > 0 && D % 4 == 0 && D <= 128 && cap > 0 && context > 0,
                  "ring_attention: bad shape (D %% 4 == 0 and D <= 128 required)");
   const long long total = (long long)batch * T * H;
   const int warps = 4;
   ring_attention_kernel<<<ceil_div(total, warps), warps * 32, warps * D * sizeof(float), (cudaStream_t)stream>>>(
-      qkv, kv, (const long long*)offset, out, batch, T, H, D, cap, context);
+      qkv, kv, (const long long*)offset, out, batch, T, H, D, cap, context, linear);
   count_launch();
   return check_launch("ring_attention");
 }

@@ -104,10 +104,10 @@ def rope_kv_append(qkv, kv, offset, freqs, batch, T, H, D, cap):
                                                     batch, T, H, D, cap, _stream()), "rope_kv_append")
 
 
-def ring_attention(qkv, kv, offset, out, batch, T, H, D, cap, context):
+def ring_attention(qkv, kv, offset, out, batch, T, H, D, cap, context, linear):
     _cuda(qkv, kv, offset, out)
     _lib.check(_lib.lib().rstnet_ring_attention_f32(qkv.data_ptr(), kv.data_ptr(), offset.data_ptr(), out.data_ptr(),
-                                                    batch, T, H, D, cap, context, _stream()), "ring_attention")
+                                                    batch, T, H, D, cap, context, int(linear), _stream()), "ring_attention")
 
 
 def rvq_encode_workspace(N, n_q, dim, bins) -> int:

@@ -176,7 +176,7 @@ def test_rope_ring_attention_vs_oracle(T, steps, cap, context):
         qd = qkv.to(DEV).contiguous()
         out = torch.empty(B, T, H * D, device=DEV)
         ops.rope_kv_append(qd, kv, offset, freqs, B, T, H, D, cap)
-        ops.ring_attention(qd, kv, offset, out, B, T, H, D, cap, context)
+        ops.ring_attention(qd, kv, offset, out, B, T, H, D, cap, context, ring is None)
         ops.counter_add(offset, T)
         off += T
         if step in (0, steps // 2, steps - 1):
