@@ -60,6 +60,39 @@ typedef struct {
 } rstnet_gemm_rows_args;
 int rstnet_gemm_rows_f32(const rstnet_gemm_rows_args* args, rstnet_stream_t stream);
 
+/* ---- the same contraction on the 5th-gen tensor cores (tcgen05.mma, accumulator in TMEM, operands
+ * staged by TMA), as a plan bound to fixed buffers (the library owns only the TMA descriptors and
+ * tile configuration; the caller owns all tensors):
+ *   D[(i,o), n] = sum_tap sum_c A[c, i + tap*tap_di, o*o_mul + tap*tap_do] * W[n, tap*Kc + c]
+ * A is the activation buffer viewed as a 3-D tensor (c, i, o) with element strides
+ * (1, a_i_stride, a_o_stride); W is [N][taps*Kc] (K contiguous).  Output element (i, o, n) goes to
+ * C + o*c_o_stride + i*c_i_stride + n, or, when n_split > 0 (transposed conv: n = j*n_split + co),
+ * to C + o*c_o_stride + i*c_i_stride + j*c_split_stride + co; R (optional residual) likewise.
+ * Epilogue: post(R + scale*(acc + bias)); pre_act is applied to A in shared memory.
+ * precision 0 = 3xTF32 split (fp32-equivalent, for RVQ-index exactness), 1 = single TF32 pass.
+ * Same reference call sites as rstnet_gemm_rows_f32. */
+typedef struct rstnet_tc_plan rstnet_tc_plan;
+typedef struct {
+  const float* A;
+  int64_t a_i_stride, a_o_stride;
+  int32_t a_c_extent, a_i_extent, a_o_extent;
+  int32_t taps, tap_di, tap_do, o_mul;
+  const float* W;
+  int32_t N, Kc;
+  int32_t I_out, O_out;
+  float* C;
+  int64_t c_i_stride, c_o_stride, c_split_stride;
+  const float* R;
+  int64_t r_i_stride, r_o_stride, r_split_stride;
+  const float* bias;
+  const float* scale;
+  int32_t n_split;
+  int32_t pre_act, post_act, precision;
+} rstnet_tc_gemm_desc;
+int rstnet_tc_gemm_create(const rstnet_tc_gemm_desc* desc, rstnet_tc_plan** out);
+int rstnet_tc_gemm_run(const rstnet_tc_plan* plan, rstnet_stream_t stream);
+void rstnet_tc_gemm_destroy(rstnet_tc_plan* plan);
+
 /* ---- first SEANet encoder conv, Cin == 1 (modules/seanet.py:177-187): x [B, xrows] (padded,
  * xrows >= T + k - 1), w [Cout][k], out rows at out + b*out_batch_stride + t*Cout. */
 int rstnet_conv1d_cin1_f32(const float* x, int64_t x_batch_stride, const float* w, const float* bias,

@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import ACT_ELU, ACT_GELU, ACT_NONE, GemmRowsArgs, RowCopy  # noqa: F401
+from ._lib import ACT_ELU, ACT_GELU, ACT_NONE, GemmRowsArgs, RowCopy, TcGemmDesc  # noqa: F401
 
 
 def _stream() -> int:
@@ -47,6 +47,48 @@ def gemm_rows(A: torch.Tensor, a_off: int, a_bs: int, a_rs: int, Wt: torch.Tenso
     a.batch, a.rows, a.N, a.K = batch, rows, N, K
     a.pre_act, a.post_act = pre_act, post_act
     _lib.check(_lib.lib().rstnet_gemm_rows_f32(C.byref(a), _stream()), "gemm_rows_f32")
+
+
+class TcGemm:
+    """A tcgen05 GEMM plan bound to fixed buffers (rstnet_tc_gemm_create / run / destroy).
+
+    D[(i,o), n] = sum_tap sum_c A[c, i + tap*tap_di, o*o_mul + tap*tap_do] * W[n, tap*Kc + c];
+    offsets / strides in elements; see include/rstnet_b200.h."""
+
+    def __init__(self, A, a_off, a_i_stride, a_o_stride, a_c_extent, a_i_extent, a_o_extent, W, Kc, C_, c_off, c_i_stride,
+                 c_o_stride, I_out, O_out, *, taps=1, tap_di=0, tap_do=0, o_mul=1, bias=None, scale=None, R=None, r_off=0,
+                 r_i_stride=0, r_o_stride=0, n_split=0, c_split_stride=0, r_split_stride=0, pre_act=ACT_NONE,
+                 post_act=ACT_NONE, precision=0):
+        _cuda(A, W, C_, bias, scale, R)
+        N, Ktot = W.shape
+        assert Ktot == taps * Kc, (Ktot, taps, Kc)
+        d = TcGemmDesc()
+        d.A = A.data_ptr() + 4 * a_off
+        d.a_i_stride, d.a_o_stride = a_i_stride, a_o_stride
+        d.a_c_extent, d.a_i_extent, d.a_o_extent = a_c_extent, a_i_extent, a_o_extent
+        d.taps, d.tap_di, d.tap_do, d.o_mul = taps, tap_di, tap_do, o_mul
+        d.W, d.N, d.Kc, d.I_out, d.O_out = W.data_ptr(), N, Kc, I_out, O_out
+        d.C = C_.data_ptr() + 4 * c_off
+        d.c_i_stride, d.c_o_stride, d.c_split_stride = c_i_stride, c_o_stride, c_split_stride
+        d.R = None if R is None else R.data_ptr() + 4 * r_off
+        d.r_i_stride, d.r_o_stride, d.r_split_stride = r_i_stride, r_o_stride, r_split_stride
+        d.bias, d.scale = _p(bias), _p(scale)
+        d.n_split, d.pre_act, d.post_act, d.precision = n_split, pre_act, post_act, precision
+        self._keep = (A, W, C_, bias, scale, R)  # the plan embeds raw pointers
+        self._h = C.c_void_p()
+        _lib.check(_lib.lib().rstnet_tc_gemm_create(C.byref(d), C.byref(self._h)), "tc_gemm_create")
+
+    def run(self):
+        _lib.check(_lib.lib().rstnet_tc_gemm_run(self._h, _stream()), "tc_gemm_run")
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.lib().rstnet_tc_gemm_destroy(h)
+            except Exception:
+                pass
+            self._h = None
 
 
 def conv1d_cin1(x, x_bs, w, bias, out, out_off, out_bs, batch, T, Cout, k, post_act=ACT_NONE):
