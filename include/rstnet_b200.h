@@ -93,23 +93,26 @@ int rstnet_tc_gemm_create(const rstnet_tc_gemm_desc* desc, rstnet_tc_plan** out)
 int rstnet_tc_gemm_run(const rstnet_tc_plan* plan, rstnet_stream_t stream);
 void rstnet_tc_gemm_destroy(rstnet_tc_plan* plan);
 
-/* ---- first SEANet encoder conv, Cin == 1 (modules/seanet.py:177-187): x [B, xrows] (padded,
- * xrows >= T + k - 1), w [Cout][k], out rows at out + b*out_batch_stride + t*Cout. */
-int rstnet_conv1d_cin1_f32(const float* x, int64_t x_batch_stride, const float* w, const float* bias,
-                           float* out, int64_t out_batch_stride, int32_t batch, int32_t T,
-                           int32_t Cout, int32_t k, int32_t post_act, rstnet_stream_t stream);
+/* ---- first SEANet encoder conv, Cin == 1 (modules/seanet.py:177-187): sample (b, t) at
+ * x + b*x_batch_stride + t*x_time_stride (padded, T + k - 1 samples per stream), w [Cout][k],
+ * out rows at out + b*out_batch_stride + t*out_time_stride. */
+int rstnet_conv1d_cin1_f32(const float* x, int64_t x_batch_stride, int64_t x_time_stride, const float* w, const float* bias,
+                           float* out, int64_t out_batch_stride, int64_t out_time_stride, int32_t batch,
+                           int32_t T, int32_t Cout, int32_t k, int32_t post_act, rstnet_stream_t stream);
 
-/* ---- last SEANet decoder conv, Cout == 1 (modules/seanet.py:372-384): x [B, rows, Cin] NWC
- * (padded, already activated), w [k*Cin] ((tap, ci) order), out [B, T]. */
-int rstnet_conv1d_cout1_f32(const float* x, int64_t x_batch_stride, const float* w, const float* bias,
-                            float* out, int64_t out_batch_stride, int32_t batch, int32_t T,
-                            int32_t Cin, int32_t k, rstnet_stream_t stream);
+/* ---- last SEANet decoder conv, Cout == 1 (modules/seanet.py:372-384): x row (b, t) =
+ * Cin floats at x + b*x_batch_stride + t*x_time_stride (padded, already activated),
+ * w [k*Cin] ((tap, ci) order), out [B, T]. */
+int rstnet_conv1d_cout1_f32(const float* x, int64_t x_batch_stride, int64_t x_time_stride, const float* w,
+                            const float* bias, float* out, int64_t out_batch_stride, int32_t batch,
+                            int32_t T, int32_t Cin, int32_t k, rstnet_stream_t stream);
 
 /* ---- ConvTrUpsample1d, depthwise ConvTranspose1d k == 2*stride, no bias
  * (modules/resample.py:86-119): x [B, 1+T, C] with one carry row in front, w [C][k],
  * out[b, t*s+j, c] = x[t]*w[c][j] + x[t-1]*w[c][j+s]. */
-int rstnet_convtr1d_depthwise_f32(const float* x, int64_t x_batch_stride, const float* w, float* out,
-                                  int64_t out_batch_stride, int32_t batch, int32_t T, int32_t C,
+int rstnet_convtr1d_depthwise_f32(const float* x, int64_t x_batch_stride, int64_t x_time_stride,
+                                  const float* w, float* out, int64_t out_batch_stride,
+                                  int64_t out_time_stride, int32_t batch, int32_t T, int32_t C,
                                   int32_t stride, rstnet_stream_t stream);
 
 /* ---- row utilities for padding / streaming carry (F.pad in conv.py:81-100;
@@ -139,7 +142,7 @@ int rstnet_layer_norm_f32(const float* x, int64_t x_batch_stride, const float* w
 
 /* ---- codec transformer attention (modules/transformer.py:375-419, modules/rope.py:11-68,
  * RingKVCache transformer.py:211-278).
- * qkv [B, T, 3*H*D] laid out (p h d).  Step 1 rotates q,k by the pair-RoPE angle of absolute
+ * qkv row (b,t) = 3*H*D floats laid out (p h d) at qkv + b*q_batch_stride + t*q_time_stride.  Step 1 rotates q,k by the pair-RoPE angle of absolute
  * position (*offset + t), writes rotated q back in place and k,v into the ring kv[2][B][H][cap][D]
  * at slot (pos % cap).  Step 2 attends each query over keys with positions in
  * (pos_q - context, pos_q] that are still in the ring, fp32 softmax, out [B, T, H*D].
@@ -147,30 +150,33 @@ int rstnet_layer_norm_f32(const float* x, int64_t x_batch_stride, const float* w
  * plain [0, cap) buffer holding every position (non-streaming, KVCacheResult.from_kv); linear == 0:
  * ring semantics of RingKVCache.complete, including its quirk that the oldest slot (position
  * end - cap) is labelled `end_offset` and therefore masked once the ring has wrapped. */
-int rstnet_rope_kv_append_f32(float* qkv, float* kv, const int64_t* offset, const float* freqs,
-                              int32_t batch, int32_t T, int32_t H, int32_t D, int32_t cap,
+int rstnet_rope_kv_append_f32(float* qkv, int64_t q_batch_stride, int64_t q_time_stride, float* kv,
+                              const int64_t* offset, const float* freqs, int32_t batch, int32_t T,
+                              int32_t H, int32_t D, int32_t cap, rstnet_stream_t stream);
+int rstnet_ring_attention_f32(const float* qkv, int64_t q_batch_stride, int64_t q_time_stride,
+                              const float* kv, const int64_t* offset, float* out,
+                              int64_t o_batch_stride, int64_t o_time_stride, int32_t batch, int32_t T,
+                              int32_t H, int32_t D, int32_t cap, int32_t context, int32_t linear,
                               rstnet_stream_t stream);
-int rstnet_ring_attention_f32(const float* qkv, const float* kv, const int64_t* offset, float* out,
-                              int32_t batch, int32_t T, int32_t H, int32_t D, int32_t cap,
-                              int32_t context, int32_t linear, rstnet_stream_t stream);
 
 /* ---- SplitResidualVectorQuantizer.encode (quantization/vq.py:305-315; core_vq.py:179-185,
  * 365-376): x [N, ldx] holds the two projected latents (rvq_first at column 0, rvq_rest at
  * column dim); Et [n_q][dim][bins] are the centroids TRANSPOSED, enorm [n_q][bins] their squared
  * norms.  Distances follow torch.cdist's matmul form sqrt(max(|x|^2+|e|^2-2x.e, 0)); argmin
- * keeps the first minimum.  codes out: int64 [B][n_q][T] with N == B*T (frame n = b*T + t).
+ * keeps the first minimum.  codes out: int64 [B][n_q][T] with N == B*T; frame n = b*T + t, or
+ * n = t*B + b when time_major != 0 (the streaming plans' [T, B, C] layout).
  * work: scratch of rstnet_rvq_encode_workspace(N, ...) bytes. */
 int64_t rstnet_rvq_encode_workspace(int64_t N, int32_t n_q, int32_t dim, int32_t bins);
 int rstnet_rvq_encode_f32(const float* x, int64_t ldx, const float* E, const float* Et,
                           const float* enorm, int64_t* codes, void* work, int64_t N, int32_t T,
                           int32_t n_q, int32_t n_q_semantic, int32_t dim, int32_t bins,
-                          rstnet_stream_t stream);
+                          int32_t time_major, rstnet_stream_t stream);
 /* ---- SplitResidualVectorQuantizer.decode gather part (vq.py:317-323; core_vq.py:198-206,
  * 378-384): q [N, 2*dim] = [ E0[c0] | sum_{l>=n_q_semantic} E_l[c_l] ]; the two output_proj are
  * then one rstnet_gemm_rows_f32 with K = 2*dim. */
 int rstnet_rvq_decode_gather_f32(const int64_t* codes, const float* E, float* q, int64_t N, int32_t T,
                                  int32_t n_q, int32_t n_q_semantic, int32_t dim, int32_t bins,
-                                 rstnet_stream_t stream);
+                                 int32_t time_major, rstnet_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -79,19 +79,19 @@ def lib() -> C.CDLL:
     L.rstnet_tc_gemm_run.argtypes = [vp, vp]
     L.rstnet_tc_gemm_destroy.argtypes = [vp]
     L.rstnet_tc_gemm_destroy.restype = None
-    L.rstnet_conv1d_cin1_f32.argtypes = [vp, i64, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp]
-    L.rstnet_conv1d_cout1_f32.argtypes = [vp, i64, vp, vp, vp, i64, i32, i32, i32, i32, vp]
-    L.rstnet_convtr1d_depthwise_f32.argtypes = [vp, i64, vp, vp, i64, i32, i32, i32, i32, vp]
+    L.rstnet_conv1d_cin1_f32.argtypes = [vp, i64, i64, vp, vp, vp, i64, i64, i32, i32, i32, i32, i32, vp]
+    L.rstnet_conv1d_cout1_f32.argtypes = [vp, i64, i64, vp, vp, vp, i64, i32, i32, i32, i32, vp]
+    L.rstnet_convtr1d_depthwise_f32.argtypes = [vp, i64, i64, vp, vp, i64, i64, i32, i32, i32, i32, vp]
     L.rstnet_rows_fill_f32.argtypes = [vp, i64, i32, i32, i32, i32, i32, i32, vp, vp]
     L.rstnet_rows_copy_table_f32.argtypes = [vp, i32, i32, vp]
     L.rstnet_counter_add.argtypes = [vp, i64, vp]
     L.rstnet_layer_norm_f32.argtypes = [vp, i64, vp, vp, vp, i32, i32, i32, f32, vp]
-    L.rstnet_rope_kv_append_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
-    L.rstnet_ring_attention_f32.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
+    L.rstnet_rope_kv_append_f32.argtypes = [vp, i64, i64, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    L.rstnet_ring_attention_f32.argtypes = [vp, i64, i64, vp, vp, vp, i64, i64, i32, i32, i32, i32, i32, i32, i32, vp]
     L.rstnet_rvq_encode_workspace.argtypes = [i64, i32, i32, i32]
     L.rstnet_rvq_encode_workspace.restype = i64
-    L.rstnet_rvq_encode_f32.argtypes = [vp, i64, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp]
-    L.rstnet_rvq_decode_gather_f32.argtypes = [vp, vp, vp, i64, i32, i32, i32, i32, i32, vp]
+    L.rstnet_rvq_encode_f32.argtypes = [vp, i64, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, vp]
+    L.rstnet_rvq_decode_gather_f32.argtypes = [vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, vp]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("rstnet_version",):

@@ -49,19 +49,6 @@ _OLD_CODEBOOK_NAMES = {"inited": "_initialized", "cluster_size": "cluster_usage"
                        "embed_sum": "embedding_sum"}  # quantization/core_vq.py:126-140
 
 
-class _Buf:
-    """[B, ctx + T + extra, C] fp32 activation buffer; rows [ctx, ctx+T) are the live rows."""
-
-    def __init__(self, B: int, ctx: int, T: int, extra: int, C: int, device):
-        self.B, self.ctx, self.T, self.extra, self.C = B, ctx, T, extra, C
-        self.rows = ctx + T + extra
-        self.t = torch.zeros(B, self.rows, C, device=device, dtype=torch.float32)
-        self.bs = self.rows * C
-
-    def off(self, row: int) -> int:
-        return row * self.C
-
-
 class MimiCodec(nn.Module):
     """Drop-in for the reference ``MimiCodec`` (same constructor arguments and defaults)."""
 
@@ -164,6 +151,10 @@ class MimiCodec(nn.Module):
         self._engine: Optional["_Engine"] = None
         self._stream_state: Optional["_StreamState"] = None
         self.use_cuda_graphs = True
+        # streaming steps run their GEMMs on the tensor cores (tcgen05, 3xTF32 = fp32-equivalent products,
+        # fp32 accumulation); False selects the fp32 FFMA kernels (bit-faithful fp32 arithmetic) there too.
+        self.streaming_tensor_cores = True
+        self.tc_precision = 0  # 0: 3xTF32, 1: single TF32 pass
 
     # ------------------------------------------------------------------ parameters
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
@@ -281,12 +272,42 @@ class MimiTokenizer:
 
 
 # ====================================================================== engine
+class _Buf:
+    """fp32 activation buffer with `ctx` left-context rows: rows [ctx, ctx+T) are live, [0, ctx) is
+    the causal padding / streaming carry, trailing `extra` rows are right padding.
+    Layout "btc": [B, rows, C] (batch-major; FFMA path).  Layout "tbc": [rows, B, C] (time-major,
+    batch-inner; a 128-row tensor-core tile = 128 streams at one time step)."""
+
+    def __init__(self, B: int, ctx: int, T: int, extra: int, C: int, device, tbc: bool):
+        self.B, self.ctx, self.T, self.extra, self.C, self.tbc = B, ctx, T, extra, C, tbc
+        self.rows = ctx + T + extra
+        if tbc:
+            self.t = torch.zeros(self.rows, B, C, device=device, dtype=torch.float32)
+            self.ts, self.bs = B * C, C
+        else:
+            self.t = torch.zeros(B, self.rows, C, device=device, dtype=torch.float32)
+            self.ts, self.bs = C, self.rows * C
+
+    def off(self, row: int) -> int:
+        return row * self.ts
+
+    def zero_ctx(self):
+        if self.ctx:
+            (self.t[:self.ctx] if self.tbc else self.t[:, :self.ctx]).zero_()
+
+    def carry_entry(self):
+        """row-copy table entry that moves the last ctx rows to the front (streaming carry)."""
+        if self.tbc:
+            return (self.t, 0, self.B * self.C, self.T, 0, self.ctx)
+        return (self.t, self.bs, self.C, self.T, 0, self.ctx)
+
+
 class _Engine:
     """Device-resident packed weights + launch sequences."""
 
     BATCH_MODE_BYTES = 12 << 30  # activation budget per non-streaming pass; larger batches are split
 
-    def __init__(self, m: MimiCodec, device: torch.device):
+    def __init__(self, m: "MimiCodec", device: torch.device):
         self.m, self.device = m, device
         sd = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in m.state_dict().items()}
         self.D, self.nf = m.latent_dim, m.n_filters
@@ -294,18 +315,27 @@ class _Engine:
         self.enc_ratios = list(reversed(m.ratios))
         D = self.D
 
-        def conv_w(prefix):  # [Cout,Cin,k] -> Wt[(tap,ci), co]
+        def conv_w(prefix):
+            """[Cout,Cin,k] -> Wt[(tap,ci), co] for the FFMA kernel and W[co, (tap,ci)] for tcgen05."""
             w = sd[f"{prefix}.weight"]
             cout, cin, k = w.shape
-            return w.permute(2, 1, 0).reshape(k * cin, cout).contiguous(), sd.get(f"{prefix}.bias")
+            wk = w.permute(0, 2, 1).reshape(cout, k * cin).contiguous()
+            return dict(W=wk, Wt=wk.t().contiguous(), bias=sd.get(f"{prefix}.bias"), taps=k)
 
-        def convtr_w(prefix, s):  # [Cin,Cout,2s] -> Wt[(half,ci), (j,co)], half 0 multiplies x[t-1]
+        def convtr_w(prefix, s):
+            """[Cin,Cout,2s] -> 2-tap GEMM weights: K = (half, ci) with half 0 multiplying x[t-1]
+            (kernel tap j+s) and half 1 multiplying x[t] (tap j); N = (j, co)."""
             w = sd[f"{prefix}.weight"]
             cin, cout, k = w.shape
             assert k == 2 * s
-            w_prev = w[:, :, s:].permute(0, 2, 1).reshape(cin, s * cout)
-            w_cur = w[:, :, :s].permute(0, 2, 1).reshape(cin, s * cout)
-            return torch.cat([w_prev, w_cur], 0).contiguous(), sd[f"{prefix}.bias"].repeat(s).contiguous()
+            w_prev = w[:, :, s:].permute(2, 1, 0).reshape(s * cout, cin)
+            w_cur = w[:, :, :s].permute(2, 1, 0).reshape(s * cout, cin)
+            wk = torch.cat([w_prev, w_cur], 1).contiguous()
+            return dict(W=wk, Wt=wk.t().contiguous(), bias=sd[f"{prefix}.bias"].repeat(s).contiguous(), taps=2)
+
+        def lin_w(w):
+            w = w.contiguous()
+            return dict(W=w, Wt=w.t().contiguous(), bias=None, taps=1)
 
         # ---- encoder
         self.e_conv0_w = sd["encoder.model.0.conv.conv.weight"].reshape(self.nf, -1).contiguous()
@@ -319,7 +349,7 @@ class _Engine:
             idx += 1
         idx += 1
         self.e_final = conv_w(f"encoder.model.{idx}.conv.conv")
-        self.down_w = conv_w("downsample.conv.conv.conv")[0]
+        self.down_w = conv_w("downsample.conv.conv.conv")
         # ---- decoder
         self.d_conv0 = conv_w("decoder.model.0.conv.conv")
         self.d_tr, self.d_res = [], []
@@ -342,25 +372,24 @@ class _Engine:
             for l in range(m.num_layers):
                 p = f"{side}.transformer.layers.{l}"
                 layers.append(dict(
-                    in_w=sd[f"{p}.self_attn.in_proj_weight"].t().contiguous(),
-                    out_w=sd[f"{p}.self_attn.out_proj.weight"].t().contiguous(),
+                    in_w=lin_w(sd[f"{p}.self_attn.in_proj_weight"]), out_w=lin_w(sd[f"{p}.self_attn.out_proj.weight"]),
                     n1w=sd[f"{p}.norm1.weight"], n1b=sd[f"{p}.norm1.bias"],
                     n2w=sd[f"{p}.norm2.weight"], n2b=sd[f"{p}.norm2.bias"],
-                    w1=sd[f"{p}.linear1.weight"].t().contiguous(), w2=sd[f"{p}.linear2.weight"].t().contiguous(),
+                    w1=lin_w(sd[f"{p}.linear1.weight"]), w2=lin_w(sd[f"{p}.linear2.weight"]),
                     ls1=sd[f"{p}.layer_scale_1.scale"], ls2=sd[f"{p}.layer_scale_2.scale"]))
             self.tr[side] = layers
         hd = D // m.num_heads
         # freqs exactly as rope.py:36-37 evaluates them (fp32 tensor * python scalar, then exp)
         ds = torch.arange(hd // 2, dtype=torch.float32)
         self.freqs = torch.exp(ds * (-math.log(m.max_period) * 2 / hd)).to(device)
-        # ---- quantizer
+        # ---- quantizer: both input projections as one GEMM (N = 2*cd), both output projections as one (K = 2*cd)
         cd = m.codebook_dim
         w1 = sd["quantizer.rvq_first.input_proj.weight"].reshape(cd, D)
         w2 = sd["quantizer.rvq_rest.input_proj.weight"].reshape(cd, D)
-        self.q_in_w = torch.cat([w1.t(), w2.t()], 1).contiguous()            # [D, 2cd]
+        self.q_in = lin_w(torch.cat([w1, w2], 0))                              # [2cd, D]
         o1 = sd["quantizer.rvq_first.output_proj.weight"].reshape(D, cd)
         o2 = sd["quantizer.rvq_rest.output_proj.weight"].reshape(D, cd)
-        self.q_out_w = torch.cat([o1.t(), o2.t()], 0).contiguous()           # [2cd, D]
+        self.q_out = lin_w(torch.cat([o1, o2], 1))                             # [D, 2cd]
         prefixes = [f"quantizer.rvq_first.vq.layers.{i}._codebook" for i in range(m.n_q_semantic)]
         prefixes += [f"quantizer.rvq_rest.vq.layers.{i}._codebook" for i in range(m.n_q - m.n_q_semantic)]
         # centroids = embedding_sum / cluster_usage.clamp(min=eps) (core_vq.py:142-150); the squared
@@ -373,44 +402,21 @@ class _Engine:
         self.zero_counter = torch.zeros(1, dtype=torch.int64, device=device)
         self._plans: Dict[tuple, object] = {}
 
-    # ------------------------------------------------------------------ shared launch sequences
-    def _transformer(self, side: str, X: _Buf, x_row: int, B: int, F: int, kv: List[torch.Tensor], cap: int,
-                     offset: torch.Tensor, scratch) -> None:
-        m = self.m
-        D, H = self.D, m.num_heads
-        hd = D // H
-        ln, qkv, att, ff = scratch
-        xo = X.off(x_row)
-        for l, w in enumerate(self.tr[side]):
-            kvl = kv[l] if len(kv) > 1 else kv[0]
-            ops.layer_norm(X.t, xo, X.bs, w["n1w"], w["n1b"], ln, B, F, D, 1e-5)
-            ops.gemm_rows(ln, 0, F * D, D, w["in_w"], qkv, 0, F * 3 * D, 3 * D, B, F)
-            ops.rope_kv_append(qkv, kvl, offset, self.freqs, B, F, H, hd, cap)
-            ops.ring_attention(qkv, kvl, offset, att, B, F, H, hd, cap, m.context, len(kv) == 1)
-            ops.gemm_rows(att, 0, F * D, D, w["out_w"], X.t, xo, X.bs, D, B, F, scale=w["ls1"], R=X.t, r_off=xo,
-                          r_bs=X.bs, r_rs=D)
-            ops.layer_norm(X.t, xo, X.bs, w["n2w"], w["n2b"], ln, B, F, D, 1e-5)
-            ops.gemm_rows(ln, 0, F * D, D, w["w1"], ff, 0, F * m.dim_feedforward, m.dim_feedforward, B, F, post_act=ACT_GELU)
-            ops.gemm_rows(ff, 0, F * m.dim_feedforward, m.dim_feedforward, w["w2"], X.t, xo, X.bs, D, B, F, scale=w["ls2"],
-                          R=X.t, r_off=xo, r_bs=X.bs, r_rs=D)
-
     # ------------------------------------------------------------------ plans
-    def enc_plan(self, B: int, L: int, streaming: bool) -> "_EncPlan":
-        key = ("enc", B, L, streaming)
+    def enc_plan(self, B: int, L: int) -> "_EncPlan":
+        key = ("enc", B, L)
         if key not in self._plans:
-            if not streaming:  # keep a single batch-mode plan per kind alive
-                for k in [k for k in self._plans if k[0] == "enc" and not k[3]]:
-                    del self._plans[k]
-            self._plans[key] = _EncPlan(self, B, L, streaming)
+            for k in [k for k in self._plans if k[0] == "enc"]:  # keep one batch-mode plan per kind alive
+                del self._plans[k]
+            self._plans[key] = _EncPlan(self, B, L, streaming=False, tensor_cores=False)
         return self._plans[key]
 
-    def dec_plan(self, B: int, T: int, streaming: bool) -> "_DecPlan":
-        key = ("dec", B, T, streaming)
+    def dec_plan(self, B: int, T: int) -> "_DecPlan":
+        key = ("dec", B, T)
         if key not in self._plans:
-            if not streaming:
-                for k in [k for k in self._plans if k[0] == "dec" and not k[3]]:
-                    del self._plans[k]
-            self._plans[key] = _DecPlan(self, B, T, streaming)
+            for k in [k for k in self._plans if k[0] == "dec"]:
+                del self._plans[k]
+            self._plans[key] = _DecPlan(self, B, T, streaming=False, tensor_cores=False)
         return self._plans[key]
 
     # ------------------------------------------------------------------ non-streaming entry points
@@ -424,8 +430,7 @@ class _Engine:
         outs = []
         for b0 in range(0, B, sub):
             xb = x[b0:b0 + sub]
-            plan = self.enc_plan(xb.shape[0], L, False)
-            outs.append(plan.run(xb, None).clone())
+            outs.append(self.enc_plan(xb.shape[0], L).run(xb, None).clone())
         return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
 
     def decode_batch(self, codes: torch.Tensor) -> torch.Tensor:
@@ -438,8 +443,7 @@ class _Engine:
         outs = []
         for b0 in range(0, B, sub):
             cb = codes[b0:b0 + sub].contiguous()
-            plan = self.dec_plan(cb.shape[0], T, False)
-            outs.append(plan.run(cb, None).clone())
+            outs.append(self.dec_plan(cb.shape[0], T).run(cb, None).clone())
         return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
 
 
@@ -447,192 +451,272 @@ def _ceil_div(a: int, b: int) -> int:
     return -(-a // b)
 
 
-class _EncPlan:
+class _Plan:
+    """Common machinery: a plan is a list of launch closures over static buffers.
+
+    tensor_cores=False: [B, rows, C] buffers + the fp32 FFMA strided-row GEMM (exact fp32 arithmetic;
+    any batch / clip length).  tensor_cores=True: [rows, B, C] buffers + tcgen05 3xTF32 GEMM plans
+    (streaming steps: every 128-row tile is 128 streams at one time step)."""
+
+    def __init__(self, eng: _Engine, B: int, streaming: bool, tensor_cores: bool):
+        self.eng, self.B, self.streaming, self.tc = eng, B, streaming, tensor_cores
+        self.ops_list = []
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.precision = eng.m.tc_precision
+
+    def buf(self, ctx, T, extra, C) -> _Buf:
+        return _Buf(self.B, ctx, T, extra, C, self.eng.device, self.tc)
+
+    def add(self, fn):
+        self.ops_list.append(fn)
+
+    def launch(self):
+        for fn in self.ops_list:
+            fn()
+
+    # ---- conv / transposed conv over a _Buf (taps along time)
+    def conv(self, A: _Buf, a_row0: int, stride: int, pack, out: _Buf, out_row0: int, T_out: int, *, pre=ACT_NONE,
+             post=ACT_NONE, R: Optional[_Buf] = None, r_row0: int = 0, tr_stride: int = 0):
+        B, Cin = self.B, A.C
+        taps = pack["taps"]
+        N = pack["W"].shape[0]
+        if not self.tc:
+            kw = dict(bias=pack["bias"], pre_act=pre, post_act=post)
+            if R is not None:
+                kw.update(R=R.t, r_off=R.off(r_row0), r_bs=R.bs, r_rs=R.ts)
+            self.add(lambda: ops.gemm_rows(A.t, A.off(a_row0), A.bs, stride * Cin, pack["Wt"], out.t, out.off(out_row0),
+                                           out.bs, N, B, T_out, **kw))
+            return
+        kw = dict(taps=taps, tap_do=1, o_mul=stride, bias=pack["bias"], pre_act=pre, post_act=post, precision=self.precision)
+        if R is not None:
+            kw.update(R=R.t, r_off=R.off(r_row0), r_i_stride=R.C, r_o_stride=B * R.C)
+        if tr_stride:
+            kw.update(n_split=out.C, c_split_stride=B * out.C)
+        plan = ops.TcGemm(A.t, A.off(a_row0), Cin, B * Cin, Cin, B, A.rows - a_row0, pack["W"], Cin, out.t, out.off(out_row0),
+                          out.C, (tr_stride or 1) * B * out.C, B, T_out, **kw)
+        self.add(plan.run)
+
+    # ---- linear over `rows` consecutive rows
+    def linear(self, A_t, a_rows_view, K, pack, out_t, out_view, N_row_stride, *, post=ACT_NONE, scale=None, R_view=None):
+        """a_rows_view / out_view / R_view: (offset, batch, rows_per_batch, batch_stride) with row stride K / N_row_stride."""
+        a_off, nb, rpb, a_bs = a_rows_view
+        c_off, _, _, c_bs = out_view
+        if not self.tc:
+            kw = dict(post_act=post, scale=scale)
+            if R_view is not None:
+                kw.update(R=out_t, r_off=R_view[0], r_bs=R_view[3], r_rs=N_row_stride)
+            self.add(lambda: ops.gemm_rows(A_t, a_off, a_bs, K, pack["Wt"], out_t, c_off, c_bs, N_row_stride, nb, rpb, **kw))
+            return
+        assert nb == 1
+        kw = dict(post_act=post, scale=scale, precision=self.precision)
+        if R_view is not None:
+            kw.update(R=out_t, r_off=R_view[0], r_i_stride=N_row_stride, r_o_stride=rpb * N_row_stride)
+        plan = ops.TcGemm(A_t, a_off, K, rpb * K, K, rpb, 1, pack["W"], K, out_t, c_off, N_row_stride, rpb * N_row_stride, rpb, 1, **kw)
+        self.add(plan.run)
+
+    def rows_view(self, X: _Buf, row0: int, nrows: int):
+        """(offset, batch, rows_per_batch, batch_stride) of rows [row0, row0+nrows) of every stream."""
+        if self.tc:
+            return (X.off(row0), 1, nrows * self.B, 0)
+        return (X.off(row0), self.B, nrows, X.bs)
+
+    def flat_view(self, nrows: int, width: int):
+        """a contiguous [B*nrows, width] scratch in the plan's row order."""
+        if self.tc:
+            return (0, 1, nrows * self.B, 0)
+        return (0, self.B, nrows, nrows * width)
+
+    # ---- the 8-layer codec transformer, in place on rows [x_row, x_row+F) of X
+    def transformer(self, side: str, X: _Buf, x_row: int, F: int):
+        eng, m, B = self.eng, self.eng.m, self.B
+        D, H, FF = eng.D, m.num_heads, m.dim_feedforward
+        hd = D // H
+        dev = eng.device
+        ln = torch.empty(B * F, D, device=dev)
+        qkv = torch.empty(B * F, 3 * D, device=dev)
+        att = torch.empty(B * F, D, device=dev)
+        ff = torch.empty(B * F, FF, device=dev)
+        self.scratch = (ln, qkv, att, ff)
+        if self.streaming:
+            cap = m.context
+            kv = [torch.zeros(2, B, H, cap, hd, device=dev) for _ in range(m.num_layers)]
+            offset = torch.zeros(1, dtype=torch.int64, device=dev)
+        else:
+            cap = F
+            kv = [torch.zeros(2, B, H, cap, hd, device=dev)] * m.num_layers
+            offset = eng.zero_counter
+        self.kv, self.offset, self.cap = kv, offset, cap
+        xv = self.rows_view(X, x_row, F)
+        if self.tc:
+            q_bs, q_ts, o_bs, o_ts = 3 * D, B * 3 * D, D, B * D
+            ln_args = (1, F * B)
+        else:
+            q_bs, q_ts, o_bs, o_ts = F * 3 * D, 3 * D, F * D, D
+            ln_args = (B, F)
+        x_bs = 0 if self.tc else X.bs
+        linear = not self.streaming
+        for l, w in enumerate(eng.tr[side]):
+            kvl = kv[l]
+            self.add(lambda w=w: ops.layer_norm(X.t, xv[0], x_bs, w["n1w"], w["n1b"], ln, ln_args[0], ln_args[1], D, 1e-5))
+            self.linear(ln, self.flat_view(F, D), D, w["in_w"], qkv, self.flat_view(F, 3 * D), 3 * D)
+            self.add(lambda kvl=kvl: ops.rope_kv_append(qkv, q_bs, q_ts, kvl, offset, eng.freqs, B, F, H, hd, cap))
+            self.add(lambda kvl=kvl: ops.ring_attention(qkv, q_bs, q_ts, kvl, offset, att, o_bs, o_ts, B, F, H, hd, cap, m.context, linear))
+            self.linear(att, self.flat_view(F, D), D, w["out_w"], X.t, xv, D, scale=w["ls1"], R_view=xv)
+            self.add(lambda w=w: ops.layer_norm(X.t, xv[0], x_bs, w["n2w"], w["n2b"], ln, ln_args[0], ln_args[1], D, 1e-5))
+            self.linear(ln, self.flat_view(F, D), D, w["w1"], ff, self.flat_view(F, FF), FF, post=ACT_GELU)
+            self.linear(ff, self.flat_view(F, FF), FF, w["w2"], X.t, xv, D, scale=w["ls2"], R_view=xv)
+
+    def finish_streaming(self, carries: List[_Buf], F: int):
+        if not self.streaming:
+            return
+        dev = self.eng.device
+        self.carries = carries
+        entries = [b.carry_entry() for b in carries if b.ctx]
+        table = ops.make_copy_table(entries, dev)
+        n, nb = len(entries), (1 if self.tc else self.B)
+        self.copy_table = table
+        self.add(lambda: ops.rows_copy_table(table, n, nb))
+        self.add(lambda: ops.counter_add(self.offset, F))
+
+    def reset(self):
+        assert self.streaming
+        for b in self.carries:
+            b.zero_ctx()
+        self.offset.zero_()
+
+
+class _EncPlan(_Plan):
     """Buffers + launch order of one encode pass (whole clip, or one streaming chunk)."""
 
-    def __init__(self, eng: _Engine, B: int, L: int, streaming: bool):
+    def __init__(self, eng: _Engine, B: int, L: int, streaming: bool, tensor_cores: bool):
+        super().__init__(eng, B, streaming, tensor_cores)
         m, dev = eng.m, eng.device
-        self.eng, self.B, self.L, self.streaming = eng, B, L, streaming
+        self.L = L
         if streaming and L % m.frame_size != 0:
             raise RstnetError(f"streaming chunks must be multiples of {m.frame_size} samples, got {L}")
         nf, D = eng.nf, eng.D
         k0 = m.kernel_size
-        self.Ts = [L]
+        T = [L]
         for r in eng.enc_ratios:
-            self.Ts.append(_ceil_div(self.Ts[-1], r))
-        T = self.Ts
-        self.F = T[-1]
+            T.append(_ceil_div(T[-1], r))
+        self.F = F = T[-1]
         s = m.resample_stride
-        self.T5 = _ceil_div(self.F, s)
-        self.xin = _Buf(B, k0 - 1, L, 0, 1, dev)
-        self.y, self.h, self.r = [], [], []
+        self.T5 = T5 = _ceil_div(F, s)
+        self.xin = xin = self.buf(k0 - 1, L, 0, 1)
+        y, h, r_ = [], [], []
         C = nf
         for i, ratio in enumerate(eng.enc_ratios):
-            self.y.append(_Buf(B, m.residual_kernel_size - 1, T[i], 0, C, dev))
-            self.h.append(_Buf(B, 0, T[i], 0, C // m.compress, dev))
-            self.r.append(_Buf(B, ratio, T[i], T[i + 1] * ratio - T[i], C, dev))
+            y.append(self.buf(m.residual_kernel_size - 1, T[i], 0, C))
+            h.append(self.buf(0, T[i], 0, C // m.compress))
+            r_.append(self.buf(ratio, T[i], T[i + 1] * ratio - T[i], C))
             C *= 2
-        self.y4 = _Buf(B, m.last_kernel_size - 1, self.F, 0, C, dev)
-        self.xtr = _Buf(B, s, self.F, self.T5 * s - self.F, D, dev)
-        F = self.F
-        self.scratch = (torch.empty(B * F, D, device=dev), torch.empty(B * F, 3 * D, device=dev),
-                        torch.empty(B * F, D, device=dev), torch.empty(B * F, m.dim_feedforward, device=dev))
-        self.lat = torch.empty(B * self.T5, D, device=dev)
-        self.xproj = torch.empty(B * self.T5, 2 * m.codebook_dim, device=dev)
-        self.codes = torch.zeros(B, m.n_q, self.T5, dtype=torch.int64, device=dev)
-        self.work = torch.empty(ops.rvq_encode_workspace(B * self.T5, m.n_q, m.codebook_dim, m.codebook_size),
-                                dtype=torch.uint8, device=dev)
-        hd = D // m.num_heads
-        if streaming:
-            self.cap = m.context
-            self.kv = [torch.zeros(2, B, m.num_heads, self.cap, hd, device=dev) for _ in range(m.num_layers)]
-            self.offset = torch.zeros(1, dtype=torch.int64, device=dev)
-            carries = [self.xin] + self.y + self.r + [self.y4, self.xtr]
-            self.n_copy = len(carries)
-            self.copy_table = ops.make_copy_table([(b.t, b.bs, b.C, b.T, 0, b.ctx) for b in carries], dev)
-        else:
-            self.cap = F
-            self.kv = [torch.zeros(2, B, m.num_heads, self.cap, hd, device=dev)]
-            self.offset = eng.zero_counter
-        self.graph: Optional[torch.cuda.CUDAGraph] = None
-
-    def reset(self):
-        assert self.streaming
-        for b in [self.xin] + self.y + self.r + [self.y4, self.xtr]:
-            b.t[:, :b.ctx].zero_()
-        self.offset.zero_()
-
-    def launch(self):
-        eng, m, B = self.eng, self.eng.m, self.B
-        T, D = self.Ts, eng.D
-        k0 = m.kernel_size
-        # conv0: 1 -> nf, k7
-        ops.conv1d_cin1(self.xin.t, self.xin.bs, eng.e_conv0_w, eng.e_conv0_b, self.y[0].t, self.y[0].off(self.y[0].ctx),
-                        self.y[0].bs, B, T[0], eng.nf, k0, ACT_NONE)
-        C = eng.nf
-        for i, ratio in enumerate(eng.enc_ratios):
-            y, h, r = self.y[i], self.h[i], self.r[i]
-            (w1, b1), (w2, b2) = eng.e_res[i]
-            # SEANetResnetBlock: ELU -> k3 -> ELU -> k1, + skip; the ELU that follows is fused as post_act
-            ops.gemm_rows(y.t, 0, y.bs, C, w1, h.t, 0, h.bs, h.C, B, T[i], bias=b1, pre_act=ACT_ELU, post_act=ACT_ELU)
-            ops.gemm_rows(h.t, 0, h.bs, h.C, w2, r.t, r.off(r.ctx), r.bs, C, B, T[i], bias=b2, R=y.t, r_off=y.off(y.ctx),
-                          r_bs=y.bs, r_rs=C, post_act=ACT_ELU)
-            wd, bd = eng.e_down[i]
-            nxt = self.y[i + 1] if i + 1 < len(self.y) else self.y4
-            ops.gemm_rows(r.t, 0, r.bs, ratio * C, wd, nxt.t, nxt.off(nxt.ctx), nxt.bs, 2 * C, B, T[i + 1], bias=bd,
-                          post_act=ACT_NONE if nxt is not self.y4 else ACT_ELU)
-            C *= 2
-        wf, bf = eng.e_final
-        X = self.xtr
-        ops.gemm_rows(self.y4.t, 0, self.y4.bs, C, wf, X.t, X.off(X.ctx), X.bs, D, B, self.F, bias=bf)
-        eng._transformer("encoder_transformer", X, X.ctx, B, self.F, self.kv, self.cap, self.offset, self.scratch)
-        # ConvDownsample1d: replicate padding (left on the first call only when streaming)
-        ops.rows_fill(X.t, X.bs, B, D, 0, X.ctx, mode=1, src_row=X.ctx, only_if_zero=self.offset if self.streaming else None)
-        if X.extra:
-            ops.rows_fill(X.t, X.bs, B, D, X.ctx + X.T, X.extra, mode=1, src_row=X.ctx + X.T - 1)
-        s = m.resample_stride
-        ops.gemm_rows(X.t, 0, X.bs, s * D, eng.down_w, self.lat, 0, self.T5 * D, D, B, self.T5)
+        y4 = self.buf(m.last_kernel_size - 1, F, 0, C)
+        X = self.buf(s, F, T5 * s - F, D)
         cd = m.codebook_dim
-        ops.gemm_rows(self.lat, 0, self.T5 * D, D, eng.q_in_w, self.xproj, 0, self.T5 * 2 * cd, 2 * cd, B, self.T5)
-        ops.rvq_encode(self.xproj, 2 * cd, eng.E, eng.Et, eng.enorm, self.codes, self.work, B * self.T5, self.T5, m.n_q,
-                       m.n_q_semantic, cd, m.codebook_size)
-        if self.streaming:
-            ops.rows_copy_table(self.copy_table, self.n_copy, B)
-            ops.counter_add(self.offset, self.F)
+        self.lat = lat = torch.empty(B * T5, D, device=dev)
+        xproj = torch.empty(B * T5, 2 * cd, device=dev)
+        self.codes = codes = torch.zeros(B, m.n_q, T5, dtype=torch.int64, device=dev)
+        work = torch.empty(ops.rvq_encode_workspace(B * T5, m.n_q, cd, m.codebook_size), dtype=torch.uint8, device=dev)
+        self._keep = (xproj, work)
+
+        # conv0: 1 -> nf, k7 (HBM-bound, CUDA cores)
+        self.add(lambda: ops.conv1d_cin1(xin.t, xin.bs, xin.ts, eng.e_conv0_w, eng.e_conv0_b, y[0].t, y[0].off(y[0].ctx),
+                                         y[0].bs, y[0].ts, B, L, nf, k0, ACT_NONE))
+        for i, ratio in enumerate(eng.enc_ratios):
+            w1, w2 = eng.e_res[i]
+            # SEANetResnetBlock: ELU -> k3 -> ELU -> k1, + skip; the ELU that follows is fused as post_act
+            self.conv(y[i], 0, 1, w1, h[i], 0, T[i], pre=ACT_ELU, post=ACT_ELU)
+            self.conv(h[i], 0, 1, w2, r_[i], r_[i].ctx, T[i], post=ACT_ELU, R=y[i], r_row0=y[i].ctx)
+            nxt = y[i + 1] if i + 1 < len(y) else y4
+            self.conv(r_[i], 0, ratio, eng.e_down[i], nxt, nxt.ctx, T[i + 1], post=ACT_NONE if nxt is not y4 else ACT_ELU)
+        self.conv(y4, 0, 1, eng.e_final, X, X.ctx, F)
+        self.transformer("encoder_transformer", X, X.ctx, F)
+        # ConvDownsample1d: replicate padding (left on the first call only when streaming)
+        fill_bs, fill_nb, fill_C = (0, 1, B * D) if self.tc else (X.bs, B, D)
+        only0 = self.offset if streaming else None
+        self.add(lambda: ops.rows_fill(X.t, fill_bs, fill_nb, fill_C, 0, X.ctx, mode=1, src_row=X.ctx, only_if_zero=only0))
+        if X.extra:
+            self.add(lambda: ops.rows_fill(X.t, fill_bs, fill_nb, fill_C, X.ctx + X.T, X.extra, mode=1, src_row=X.ctx + X.T - 1))
+        lat_buf = _LatView(lat, B, T5, D, self.tc)
+        self.conv(X, 0, s, eng.down_w, lat_buf, 0, T5)
+        self.linear(lat, self.flat_view(T5, D), D, eng.q_in, xproj, self.flat_view(T5, 2 * cd), 2 * cd)
+        self.add(lambda: ops.rvq_encode(xproj, 2 * cd, eng.E, eng.Et, eng.enorm, codes, work, B * T5, T5, m.n_q, m.n_q_semantic,
+                                        cd, m.codebook_size, time_major=self.tc))
+        self.finish_streaming([xin] + y + r_ + [y4, X], F)
 
     def run(self, x: torch.Tensor, graphs: Optional[bool]) -> torch.Tensor:
-        self.xin.t[:, self.xin.ctx:self.xin.ctx + self.L, 0].copy_(x[:, 0, :])
+        xin, L = self.xin, self.L
+        if self.tc:
+            xin.t[xin.ctx:xin.ctx + L, :, 0].copy_(x[:, 0, :].t())
+        else:
+            xin.t[:, xin.ctx:xin.ctx + L, 0].copy_(x[:, 0, :])
         _run_plan(self, graphs)
         return self.codes
 
 
-class _DecPlan:
+class _LatView:
+    """Adapter so a contiguous [B*T, C] tensor can be the output `_Buf` of `_Plan.conv`."""
+
+    def __init__(self, t: torch.Tensor, B: int, T: int, C: int, tbc: bool):
+        self.t, self.C, self.ctx, self.rows, self.tbc = t, C, 0, T, tbc
+        self.ts, self.bs = (B * C, C) if tbc else (C, T * C)
+
+    def off(self, row: int) -> int:
+        return row * self.ts
+
+
+class _DecPlan(_Plan):
     """Buffers + launch order of one decode pass."""
 
-    def __init__(self, eng: _Engine, B: int, T: int, streaming: bool):
+    def __init__(self, eng: _Engine, B: int, T: int, streaming: bool, tensor_cores: bool, n_codes: Optional[int] = None):
+        super().__init__(eng, B, streaming, tensor_cores)
         m, dev = eng.m, eng.device
-        self.eng, self.B, self.T, self.streaming = eng, B, T, streaming
+        self.T = T
         D, nf = eng.D, eng.nf
         s = m.resample_stride
         self.F = F = T * s
         cd = m.codebook_dim
-        self.q = torch.empty(B * T, 2 * cd, device=dev)
-        self.qup = _Buf(B, 1, T, 0, D, dev)
-        self.xdec = _Buf(B, m.kernel_size - 1, F, 0, D, dev)
+        K = n_codes or m.n_q
+        self.codes_in = codes_in = torch.zeros(B, K, T, dtype=torch.int64, device=dev)
+        q = torch.empty(B * T, 2 * cd, device=dev)
+        qup = self.buf(1, T, 0, D)
+        X = self.buf(m.kernel_size - 1, F, 0, D)
         C = nf * 2 ** len(eng.ratios)
-        self.a = [_Buf(B, 1, F, 0, C, dev)]
-        self.yd, self.hd = [], []
+        a = [self.buf(1, F, 0, C)]
+        yd, hd_ = [], []
         Tin = F
         for i, r in enumerate(eng.ratios):
             Tout = Tin * r
-            self.yd.append(_Buf(B, m.residual_kernel_size - 1, Tout, 0, C // 2, dev))
-            self.hd.append(_Buf(B, 0, Tout, 0, C // 2 // m.compress, dev))
+            yd.append(self.buf(m.residual_kernel_size - 1, Tout, 0, C // 2))
+            hd_.append(self.buf(0, Tout, 0, C // 2 // m.compress))
             last = i == len(eng.ratios) - 1
-            self.a.append(_Buf(B, (m.last_kernel_size - 1) if last else 1, Tout, 0, C // 2, dev))
+            a.append(self.buf((m.last_kernel_size - 1) if last else 1, Tout, 0, C // 2))
             C //= 2
             Tin = Tout
-        self.Lout = Tin
-        self.wav = torch.empty(B, 1, self.Lout, device=dev)
-        self.scratch = (torch.empty(B * F, D, device=dev), torch.empty(B * F, 3 * D, device=dev),
-                        torch.empty(B * F, D, device=dev), torch.empty(B * F, m.dim_feedforward, device=dev))
-        self.codes_in = torch.zeros(B, m.n_q, T, dtype=torch.int64, device=dev)
-        hd = D // m.num_heads
-        if streaming:
-            self.cap = m.context
-            self.kv = [torch.zeros(2, B, m.num_heads, self.cap, hd, device=dev) for _ in range(m.num_layers)]
-            self.offset = torch.zeros(1, dtype=torch.int64, device=dev)
-            carries = [self.qup, self.xdec] + self.a + self.yd
-            self.n_copy = len(carries)
-            self.copy_table = ops.make_copy_table([(b.t, b.bs, b.C, b.T, 0, b.ctx) for b in carries], dev)
-        else:
-            self.cap = F
-            self.kv = [torch.zeros(2, B, m.num_heads, self.cap, hd, device=dev)]
-            self.offset = eng.zero_counter
-        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.Lout = Lout = Tin
+        self.wav = wav = torch.empty(B, 1, Lout, device=dev)
 
-    def reset(self):
-        assert self.streaming
-        for b in [self.qup, self.xdec] + self.a + self.yd:
-            b.t[:, :b.ctx].zero_()
-        self.offset.zero_()
-
-    def launch(self):
-        eng, m, B, T, F = self.eng, self.eng.m, self.B, self.T, self.F
-        D, cd = eng.D, m.codebook_dim
-        K = self.codes_in.shape[1]
-        ops.rvq_decode_gather(self.codes_in, eng.E, self.q, B * T, T, K, m.n_q_semantic, cd, m.codebook_size)
-        qup = self.qup
-        ops.gemm_rows(self.q, 0, T * 2 * cd, 2 * cd, eng.q_out_w, qup.t, qup.off(1), qup.bs, D, B, T)
-        X = self.xdec
-        ops.convtr1d_depthwise(qup.t, qup.bs, eng.up_w, X.t, X.off(X.ctx), X.bs, B, T, D, m.resample_stride)
-        eng._transformer("decoder_transformer", X, X.ctx, B, F, self.kv, self.cap, self.offset, self.scratch)
-        w0, b0 = eng.d_conv0
-        a = self.a[0]
-        ops.gemm_rows(X.t, 0, X.bs, D, w0, a.t, a.off(1), a.bs, a.C, B, F, bias=b0, post_act=ACT_ELU)
+        self.add(lambda: ops.rvq_decode_gather(codes_in, eng.E, q, B * T, T, K, m.n_q_semantic, cd, m.codebook_size,
+                                               time_major=self.tc))
+        self.linear(q, self.flat_view(T, 2 * cd), 2 * cd, eng.q_out, qup.t, self.rows_view(qup, 1, T), D)
+        self.add(lambda: ops.convtr1d_depthwise(qup.t, qup.bs, qup.ts, eng.up_w, X.t, X.off(X.ctx), X.bs, X.ts, B, T, D, s))
+        self.transformer("decoder_transformer", X, X.ctx, F)
+        self.conv(X, 0, 1, eng.d_conv0, a[0], 1, F, post=ACT_ELU)
         Tin = F
         for i, r in enumerate(eng.ratios):
-            a, y, h, nxt = self.a[i], self.yd[i], self.hd[i], self.a[i + 1]
-            wt, bt = eng.d_tr[i]
-            Cin, Cout = a.C, y.C
-            # ConvTranspose1d k=2r stride r as a GEMM over [x[t-1], x[t]]: one output row = r time steps
-            ops.gemm_rows(a.t, 0, a.bs, Cin, wt, y.t, y.off(y.ctx), y.bs, r * Cout, B, Tin, bias=bt)
+            # ConvTranspose1d k=2r stride r as a 2-tap GEMM over [x[t-1], x[t]]: one output row = r time steps
+            self.conv(a[i], 0, 1, eng.d_tr[i], yd[i], yd[i].ctx, Tin, tr_stride=r)
             Tout = Tin * r
-            (w1, b1), (w2, b2) = eng.d_res[i]
-            ops.gemm_rows(y.t, 0, y.bs, Cout, w1, h.t, 0, h.bs, h.C, B, Tout, bias=b1, pre_act=ACT_ELU, post_act=ACT_ELU)
-            ops.gemm_rows(h.t, 0, h.bs, h.C, w2, nxt.t, nxt.off(nxt.ctx), nxt.bs, Cout, B, Tout, bias=b2, R=y.t,
-                          r_off=y.off(y.ctx), r_bs=y.bs, r_rs=Cout, post_act=ACT_ELU)
+            w1, w2 = eng.d_res[i]
+            self.conv(yd[i], 0, 1, w1, hd_[i], 0, Tout, pre=ACT_ELU, post=ACT_ELU)
+            self.conv(hd_[i], 0, 1, w2, a[i + 1], a[i + 1].ctx, Tout, post=ACT_ELU, R=yd[i], r_row0=yd[i].ctx)
             Tin = Tout
-        last = self.a[-1]
-        ops.conv1d_cout1(last.t, last.bs, eng.d_final_w, eng.d_final_b, self.wav, self.Lout, B, self.Lout, last.C,
-                         m.last_kernel_size)
-        if self.streaming:
-            ops.rows_copy_table(self.copy_table, self.n_copy, B)
-            ops.counter_add(self.offset, F)
+        last = a[-1]
+        self.add(lambda: ops.conv1d_cout1(last.t, last.bs, last.ts, eng.d_final_w, eng.d_final_b, wav, Lout, B, Lout, last.C,
+                                          m.last_kernel_size))
+        self.finish_streaming([qup, X] + a + yd, F)
 
     def run(self, codes: torch.Tensor, graphs: Optional[bool]) -> torch.Tensor:
-        if codes.shape[1] != self.codes_in.shape[1]:
-            self.codes_in = torch.zeros(self.B, codes.shape[1], self.T, dtype=torch.int64, device=self.eng.device)
-            self.graph = None
         self.codes_in.copy_(codes)
         _run_plan(self, graphs)
         return self.wav
@@ -675,7 +759,7 @@ class _StreamState:
         if L not in self.enc:
             if self.enc:
                 raise RstnetError("the chunk size must stay constant within one streaming scope")
-            self.enc[L] = _EncPlan(self.eng, B, L, True)
+            self.enc[L] = _EncPlan(self.eng, B, L, True, self.eng.m.streaming_tensor_cores)
         return self.enc[L].run(x, self.eng.m.use_cuda_graphs).clone()
 
     def decode(self, codes: torch.Tensor) -> torch.Tensor:
@@ -685,7 +769,7 @@ class _StreamState:
         if T not in self.dec:
             if self.dec:
                 raise RstnetError("the chunk size must stay constant within one streaming scope")
-            self.dec[T] = _DecPlan(self.eng, B, T, True)
+            self.dec[T] = _DecPlan(self.eng, B, T, True, self.eng.m.streaming_tensor_cores, n_codes=K)
         return self.dec[T].run(codes, self.eng.m.use_cuda_graphs).clone()
 
     def reset(self):

@@ -9,8 +9,9 @@ namespace rstnet {
 extern void count_launch();
 
 // one warp per (b, t, h); lanes stride over the D/2 rotation pairs
-__global__ void rope_kv_append_kernel(float* __restrict__ qkv, float* __restrict__ kv, const long long* __restrict__ offset,
-                                      const float* __restrict__ freqs, int B, int T, int H, int D, int cap) {
+__global__ void rope_kv_append_kernel(float* __restrict__ qkv, long long qbs, long long qts, float* __restrict__ kv,
+                                      const long long* __restrict__ offset, const float* __restrict__ freqs, int B, int T,
+                                      int H, int D, int cap) {
   const long long wid = (long long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   const long long total = (long long)B * T * H;
@@ -21,7 +22,7 @@ __global__ void rope_kv_append_kernel(float* __restrict__ qkv, float* __restrict
   const long long pos = *offset + t;
   const int slot = (int)(pos % cap);
   const int HD = H * D;
-  float* q = qkv + ((long long)(b * (long long)T + t) * 3) * HD + h * D;
+  float* q = qkv + b * qbs + t * qts + h * D;
   float* k = q + HD;
   const float* v = q + 2 * HD;
   float* kdst = kv + (((long long)b * H + h) * cap + slot) * D;
@@ -45,9 +46,10 @@ __global__ void rope_kv_append_kernel(float* __restrict__ qkv, float* __restrict
 
 // one warp per (b, h, tq): lane j scores key j of each 32-key block, online softmax, then the
 // lanes own output dims (lane, lane+32, ...) for the P.V accumulation (coalesced V reads).
-__global__ void ring_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ kv,
-                                      const long long* __restrict__ offset, float* __restrict__ out, int B, int T, int H,
-                                      int D, int cap, int context, int linear) {
+__global__ void ring_attention_kernel(const float* __restrict__ qkv, long long qbs, long long qts,
+                                      const float* __restrict__ kv, const long long* __restrict__ offset,
+                                      float* __restrict__ out, long long obs, long long ots, int B, int T, int H, int D, int cap,
+                                      int context, int linear) {
   extern __shared__ __align__(16) float qs_all[];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const long long wid = (long long)blockIdx.x * (blockDim.x / 32) + warp;
@@ -59,7 +61,7 @@ __global__ void ring_attention_kernel(const float* __restrict__ qkv, const float
     h = (int)(wid % H);
     t = (int)((wid / H) % T);
     b = (int)(wid / ((long long)H * T));
-    const float* q = qkv + ((long long)(b * (long long)T + t) * 3) * H * D + h * D;
+    const float* q = qkv + b * qbs + t * qts + h * D;
     for (int d = lane; d < D; d += 32) qs[d] = q[d];
   }
   __syncwarp();
@@ -114,7 +116,7 @@ __global__ void ring_attention_kernel(const float* __restrict__ qkv, const float
     }
     m = m_new;
   }
-  float* o = out + ((long long)b * T + t) * H * D + h * D;
+  float* o = out + b * obs + t * ots + h * D;
   const float inv = 1.0f / l;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -126,20 +128,22 @@ __global__ void ring_attention_kernel(const float* __restrict__ qkv, const float
 }  // namespace rstnet
 using namespace rstnet;
 
-extern "C" int rstnet_rope_kv_append_f32(float* qkv, float* kv, const int64_t* offset, const float* freqs, int32_t batch,
-                                         int32_t T, int32_t H, int32_t D, int32_t cap, rstnet_stream_t stream) {
+extern "C" int rstnet_rope_kv_append_f32(float* qkv, int64_t q_batch_stride, int64_t q_time_stride, float* kv,
+                                         const int64_t* offset, const float* freqs, int32_t batch, int32_t T, int32_t H,
+                                         int32_t D, int32_t cap, rstnet_stream_t stream) {
   RSTNET_REQUIRE(qkv && kv && offset && freqs, "rope_kv_append: null pointer");
   RSTNET_REQUIRE(batch > 0 && T > 0 && H > 0 && D > 0 && D % 2 == 0 && cap > 0, "rope_kv_append: bad shape");
   RSTNET_REQUIRE(T <= cap, "rope_kv_append: T (%d) exceeds ring capacity (%d)", T, cap);
   const long long total = (long long)batch * T * H;
   const int warps = 8;
   rope_kv_append_kernel<<<ceil_div(total, warps), warps * 32, 0, (cudaStream_t)stream>>>(
-      qkv, kv, (const long long*)offset, freqs, batch, T, H, D, cap);
+      qkv, q_batch_stride, q_time_stride, kv, (const long long*)offset, freqs, batch, T, H, D, cap);
   count_launch();
   return check_launch("rope_kv_append");
 }
 
-extern "C" int rstnet_ring_attention_f32(const float* qkv, const float* kv, const int64_t* offset, float* out,
+extern "C" int rstnet_ring_attention_f32(const float* qkv, int64_t q_batch_stride, int64_t q_time_stride, const float* kv,
+                                         const int64_t* offset, float* out, int64_t o_batch_stride, int64_t o_time_stride,
                                          int32_t batch, int32_t T, int32_t H, int32_t D, int32_t cap, int32_t context,
                                          int32_t linear, rstnet_stream_t stream) {
   RSTNET_REQUIRE(qkv && kv && offset && out, "ring_attention: null pointer");
@@ -148,7 +152,8 @@ extern "C" int rstnet_ring_attention_f32(const float* qkv, const float* kv, cons
   const long long total = (long long)batch * T * H;
   const int warps = 4;
   ring_attention_kernel<<<ceil_div(total, warps), warps * 32, warps * D * sizeof(float), (cudaStream_t)stream>>>(
-      qkv, kv, (const long long*)offset, out, batch, T, H, D, cap, context, linear);
+      qkv, q_batch_stride, q_time_stride, kv, (const long long*)offset, out, o_batch_stride, o_time_stride, batch, T, H, D,
+      cap, context, linear);
   count_launch();
   return check_launch("ring_attention");
 }

@@ -9,8 +9,8 @@ extern void count_launch();
 // ---------------------------------------------------------------- conv Cin == 1
 // block = (Cout threads in x) x (TT time steps in y-loop); x window staged in smem.
 template <int TT>
-__global__ void conv_cin1_kernel(const float* __restrict__ x, long long xbs, const float* __restrict__ w,
-                                 const float* __restrict__ bias, float* __restrict__ out, long long obs,
+__global__ void conv_cin1_kernel(const float* __restrict__ x, long long xbs, long long xts, const float* __restrict__ w,
+                                 const float* __restrict__ bias, float* __restrict__ out, long long obs, long long ots,
                                  int T, int Cout, int k, int post_act) {
   extern __shared__ float xs[];  // TT + k - 1
   const int b = blockIdx.y;
@@ -18,7 +18,7 @@ __global__ void conv_cin1_kernel(const float* __restrict__ x, long long xbs, con
   const int nthreads = blockDim.x;
   const float* xb = x + (long long)b * xbs;
   const int nwin = min((long long)TT, (long long)T - t0) + k - 1;
-  for (int i = threadIdx.x; i < nwin; i += nthreads) xs[i] = xb[t0 + i];
+  for (int i = threadIdx.x; i < nwin; i += nthreads) xs[i] = xb[(t0 + i) * xts];
   __syncthreads();
   for (int co = threadIdx.x; co < Cout; co += nthreads) {
     float wr[16];
@@ -32,14 +32,14 @@ __global__ void conv_cin1_kernel(const float* __restrict__ x, long long xbs, con
       for (int j = 0; j < 16; ++j)
         if (j < k) acc = fmaf(xs[t + j], wr[j], acc);
       acc += bv;
-      out[(long long)b * obs + (t0 + t) * Cout + co] = apply_act(acc, post_act);
+      out[(long long)b * obs + (t0 + t) * ots + co] = apply_act(acc, post_act);
     }
   }
 }
 
 // ---------------------------------------------------------------- conv Cout == 1
 // one warp per 32 consecutive outputs; rows staged in smem padded to Cin+1 floats.
-__global__ void conv_cout1_kernel(const float* __restrict__ x, long long xbs, const float* __restrict__ w,
+__global__ void conv_cout1_kernel(const float* __restrict__ x, long long xbs, long long xts, const float* __restrict__ w,
                                   const float* __restrict__ bias, float* __restrict__ out, long long obs,
                                   int T, int Cin, int k) {
   extern __shared__ float sm[];
@@ -57,7 +57,7 @@ __global__ void conv_cout1_kernel(const float* __restrict__ x, long long xbs, co
     const int total = nrows * Cin;
     for (int i = lane; i < total; i += 32) {
       int r = i / Cin, c = i % Cin;
-      xs[r * (Cin + 1) + c] = xb[t0 * Cin + i];
+      xs[r * (Cin + 1) + c] = xb[(t0 + r) * xts + c];
     }
   }
   __syncthreads();
@@ -75,8 +75,9 @@ __global__ void conv_cout1_kernel(const float* __restrict__ x, long long xbs, co
 }
 
 // ---------------------------------------------------------------- depthwise transposed conv, k = 2*stride
-__global__ void convtr_depthwise_kernel(const float* __restrict__ x, long long xbs, const float* __restrict__ w,
-                                        float* __restrict__ out, long long obs, int T, int C, int s) {
+__global__ void convtr_depthwise_kernel(const float* __restrict__ x, long long xbs, long long xts,
+                                        const float* __restrict__ w, float* __restrict__ out, long long obs,
+                                        long long ots, int T, int C, int s) {
   const long long total = (long long)T * s * C;
   const int b = blockIdx.y;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -85,10 +86,10 @@ __global__ void convtr_depthwise_kernel(const float* __restrict__ x, long long x
     const long long t = tau / s;
     const int j = (int)(tau % s);
     const float* xb = x + (long long)b * xbs;
-    const float cur = xb[(t + 1) * C + c], prev = xb[t * C + c];  // row 0 is the carry row x[-1]
+    const float cur = xb[(t + 1) * xts + c], prev = xb[t * xts + c];  // row 0 is the carry row x[-1]
     // same association as the reference: contribution of x[t-1] (tap j+s) was accumulated first
     // (`partial`), then x[t]'s tap j is added (streaming.py:287-292)
-    out[(long long)b * obs + i] = fmaf(cur, w[c * 2 * s + j], prev * w[c * 2 * s + j + s]);
+    out[(long long)b * obs + tau * ots + c] = fmaf(cur, w[c * 2 * s + j], prev * w[c * 2 * s + j + s]);
   }
 }
 
@@ -142,22 +143,22 @@ __global__ void layer_norm_kernel(const float* __restrict__ x, long long xbs, co
 }  // namespace rstnet
 using namespace rstnet;
 
-extern "C" int rstnet_conv1d_cin1_f32(const float* x, int64_t xbs, const float* w, const float* bias, float* out,
-                                      int64_t obs, int32_t batch, int32_t T, int32_t Cout, int32_t k, int32_t post_act,
-                                      rstnet_stream_t stream) {
+extern "C" int rstnet_conv1d_cin1_f32(const float* x, int64_t xbs, int64_t xts, const float* w, const float* bias, float* out,
+                                      int64_t obs, int64_t ots, int32_t batch, int32_t T, int32_t Cout, int32_t k,
+                                      int32_t post_act, rstnet_stream_t stream) {
   RSTNET_REQUIRE(x && w && out, "conv1d_cin1: null pointer");
   RSTNET_REQUIRE(batch > 0 && T > 0 && Cout > 0 && k > 0 && k <= 16, "conv1d_cin1: bad shape (k<=16 required, k=%d)", k);
   constexpr int TT = 128;
   dim3 grid((unsigned)ceil_div(T, TT), (unsigned)batch);
   const int threads = Cout >= 128 ? 128 : (Cout >= 64 ? 64 : 32);
   conv_cin1_kernel<TT><<<grid, threads, (TT + k - 1) * sizeof(float), (cudaStream_t)stream>>>(
-      x, xbs, w, bias, out, obs, T, Cout, k, post_act);
+      x, xbs, xts, w, bias, out, obs, ots, T, Cout, k, post_act);
   count_launch();
   return check_launch("conv1d_cin1");
 }
 
-extern "C" int rstnet_conv1d_cout1_f32(const float* x, int64_t xbs, const float* w, const float* bias, float* out,
-                                       int64_t obs, int32_t batch, int32_t T, int32_t Cin, int32_t k,
+extern "C" int rstnet_conv1d_cout1_f32(const float* x, int64_t xbs, int64_t xts, const float* w, const float* bias,
+                                       float* out, int64_t obs, int32_t batch, int32_t T, int32_t Cin, int32_t k,
                                        rstnet_stream_t stream) {
   RSTNET_REQUIRE(x && w && out, "conv1d_cout1: null pointer");
   RSTNET_REQUIRE(batch > 0 && T > 0 && Cin > 0 && k > 0, "conv1d_cout1: bad shape");
@@ -167,20 +168,20 @@ extern "C" int rstnet_conv1d_cout1_f32(const float* x, int64_t xbs, const float*
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(conv_cout1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
   dim3 grid((unsigned)ceil_div(T, 32 * warps), (unsigned)batch);
-  conv_cout1_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(x, xbs, w, bias, out, obs, T, Cin, k);
+  conv_cout1_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(x, xbs, xts, w, bias, out, obs, T, Cin, k);
   count_launch();
   return check_launch("conv1d_cout1");
 }
 
-extern "C" int rstnet_convtr1d_depthwise_f32(const float* x, int64_t xbs, const float* w, float* out, int64_t obs,
-                                             int32_t batch, int32_t T, int32_t C, int32_t stride,
-                                             rstnet_stream_t stream) {
+extern "C" int rstnet_convtr1d_depthwise_f32(const float* x, int64_t xbs, int64_t xts, const float* w, float* out,
+                                             int64_t obs, int64_t ots, int32_t batch, int32_t T, int32_t C,
+                                             int32_t stride, rstnet_stream_t stream) {
   RSTNET_REQUIRE(x && w && out, "convtr1d_depthwise: null pointer");
   RSTNET_REQUIRE(batch > 0 && T > 0 && C > 0 && stride > 0, "convtr1d_depthwise: bad shape");
   const long long total = (long long)T * stride * C;
   int gx = ceil_div(total, 256);
   if (gx > 4096) gx = 4096;
-  convtr_depthwise_kernel<<<dim3(gx, batch), 256, 0, (cudaStream_t)stream>>>(x, xbs, w, out, obs, T, C, stride);
+  convtr_depthwise_kernel<<<dim3(gx, batch), 256, 0, (cudaStream_t)stream>>>(x, xbs, xts, w, out, obs, ots, T, C, stride);
   count_launch();
   return check_launch("convtr1d_depthwise");
 }

@@ -39,6 +39,7 @@ struct RvqLevelParams {
   int* pidx;
   long long N;
   int T, n_q, dim, bins, nch;
+  int time_major;  // frame n = t*B + b instead of b*T + t
 };
 
 __device__ __forceinline__ void argmin_combine(float& v, int& i, float ov, int oi) {
@@ -94,7 +95,8 @@ __global__ void __launch_bounds__(RQ_NT) rvq_level_kernel(const RvqLevelParams p
       if (lane == 0) {
         code_s[r] = (n < p.N) ? idx : 0;
         if (blockIdx.y == 0 && n < p.N) {
-          const long long b = n / p.T, t = n % p.T;
+          const long long nb = p.N / p.T;
+          const long long b = p.time_major ? n % nb : n / p.T, t = p.time_major ? n / nb : n % p.T;
           p.codes[(b * p.n_q + p.prev_level) * p.T + t] = idx;
         }
       }
@@ -199,25 +201,27 @@ __global__ void __launch_bounds__(RQ_NT) rvq_level_kernel(const RvqLevelParams p
 
 // last level of a group: reduce partials -> code
 __global__ void rvq_finish_kernel(const float* __restrict__ pval, const int* __restrict__ pidx, int nch,
-                                  long long* __restrict__ codes, int level, long long N, int T, int n_q) {
+                                  long long* __restrict__ codes, int level, long long N, int T, int n_q, int time_major) {
   const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float v = INFINITY;
   int idx = 0x7fffffff;
   for (int c = 0; c < nch; ++c) argmin_combine(v, idx, pval[n * nch + c], pidx[n * nch + c]);
-  const long long b = n / T, t = n % T;
+  const long long nb = N / T;
+  const long long b = time_major ? n % nb : n / T, t = time_major ? n / nb : n % T;
   codes[(b * n_q + level) * T + t] = idx;
 }
 
 // decode: q[n][0:dim) = sum_{l<ns} E_l[c_l];  q[n][dim:2dim) = sum_{l>=ns} E_l[c_l]  (level order)
 __global__ void rvq_gather_kernel(const long long* __restrict__ codes, const float* __restrict__ E, float* __restrict__ q,
-                                  long long N, int T, int n_q, int ns, int dim, int bins) {
+                                  long long N, int T, int n_q, int ns, int dim, int bins, int time_major) {
   const int d4n = dim / 4;
   const long long total = N * d4n;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long n = i / d4n;
     const int d4 = (int)(i % d4n);
-    const long long b = n / T, t = n % T;
+    const long long nb = N / T;
+    const long long b = time_major ? n % nb : n / T, t = time_major ? n / nb : n % T;
     float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
     for (int l = 0; l < n_q; ++l) {
       long long c = codes[(b * n_q + l) * T + t];
@@ -247,7 +251,7 @@ extern "C" int64_t rstnet_rvq_encode_workspace(int64_t N, int32_t n_q, int32_t d
 
 extern "C" int rstnet_rvq_encode_f32(const float* x, int64_t ldx, const float* E, const float* Et, const float* enorm,
                                      int64_t* codes, void* work, int64_t N, int32_t T, int32_t n_q, int32_t ns,
-                                     int32_t dim, int32_t bins, rstnet_stream_t stream) {
+                                     int32_t dim, int32_t bins, int32_t time_major, rstnet_stream_t stream) {
   RSTNET_REQUIRE(x && E && Et && enorm && codes && work, "rvq_encode: null pointer");
   RSTNET_REQUIRE(N > 0 && T > 0 && N % T == 0, "rvq_encode: N (%lld) must be a positive multiple of T (%d)", (long long)N, T);
   RSTNET_REQUIRE(n_q > 0 && ns >= 0 && ns <= n_q, "rvq_encode: bad level split");
@@ -288,14 +292,14 @@ extern "C" int rstnet_rvq_encode_f32(const float* x, int64_t ldx, const float* E
       p.enorm = enorm + (size_t)l * bins;
       p.pval = PV[g][j & 1];
       p.pidx = PI[g][j & 1];
-      p.N = N; p.T = T; p.n_q = n_q; p.dim = dim; p.bins = bins; p.nch = nch;
+      p.N = N; p.T = T; p.n_q = n_q; p.dim = dim; p.bins = bins; p.nch = nch; p.time_major = time_major;
       rvq_level_kernel<<<grid, RQ_NT, smem, st>>>(p);
       count_launch();
       if (int e = check_launch("rvq_level")) return e;
     }
     if (l1 > l0) {
       const int jl = (l1 - 1 - l0) & 1;
-      rvq_finish_kernel<<<ceil_div(N, 256), 256, 0, st>>>(PV[g][jl], PI[g][jl], nch, (long long*)codes, l1 - 1, N, T, n_q);
+      rvq_finish_kernel<<<ceil_div(N, 256), 256, 0, st>>>(PV[g][jl], PI[g][jl], nch, (long long*)codes, l1 - 1, N, T, n_q, time_major);
       count_launch();
       if (int e = check_launch("rvq_finish")) return e;
     }
@@ -304,13 +308,14 @@ extern "C" int rstnet_rvq_encode_f32(const float* x, int64_t ldx, const float* E
 }
 
 extern "C" int rstnet_rvq_decode_gather_f32(const int64_t* codes, const float* E, float* q, int64_t N, int32_t T,
-                                            int32_t n_q, int32_t ns, int32_t dim, int32_t bins, rstnet_stream_t stream) {
+                                            int32_t n_q, int32_t ns, int32_t dim, int32_t bins, int32_t time_major,
+                                            rstnet_stream_t stream) {
   RSTNET_REQUIRE(codes && E && q, "rvq_decode_gather: null pointer");
   RSTNET_REQUIRE(N > 0 && T > 0 && N % T == 0 && dim % 4 == 0, "rvq_decode_gather: bad shape");
   const long long total = (long long)N * (dim / 4);
   int gx = ceil_div(total, 256);
   if (gx > 148 * 16) gx = 148 * 16;
-  rvq_gather_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>((const long long*)codes, E, q, N, T, n_q, ns, dim, bins);
+  rvq_gather_kernel<<<gx, 256, 0, (cudaStream_t)stream>>>((const long long*)codes, E, q, N, T, n_q, ns, dim, bins, time_major);
   count_launch();
   return check_launch("rvq_decode_gather");
 }

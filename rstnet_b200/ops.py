@@ -91,22 +91,22 @@ class TcGemm:
             self._h = None
 
 
-def conv1d_cin1(x, x_bs, w, bias, out, out_off, out_bs, batch, T, Cout, k, post_act=ACT_NONE):
+def conv1d_cin1(x, x_bs, x_ts, w, bias, out, out_off, out_bs, out_ts, batch, T, Cout, k, post_act=ACT_NONE):
     _cuda(x, w, out)
-    _lib.check(_lib.lib().rstnet_conv1d_cin1_f32(x.data_ptr(), x_bs, w.data_ptr(), _p(bias), out.data_ptr() + 4 * out_off,
-                                                 out_bs, batch, T, Cout, k, post_act, _stream()), "conv1d_cin1")
+    _lib.check(_lib.lib().rstnet_conv1d_cin1_f32(x.data_ptr(), x_bs, x_ts, w.data_ptr(), _p(bias), out.data_ptr() + 4 * out_off,
+                                                 out_bs, out_ts, batch, T, Cout, k, post_act, _stream()), "conv1d_cin1")
 
 
-def conv1d_cout1(x, x_bs, w, bias, out, out_bs, batch, T, Cin, k):
+def conv1d_cout1(x, x_bs, x_ts, w, bias, out, out_bs, batch, T, Cin, k):
     _cuda(x, w, out)
-    _lib.check(_lib.lib().rstnet_conv1d_cout1_f32(x.data_ptr(), x_bs, w.data_ptr(), _p(bias), out.data_ptr(), out_bs,
+    _lib.check(_lib.lib().rstnet_conv1d_cout1_f32(x.data_ptr(), x_bs, x_ts, w.data_ptr(), _p(bias), out.data_ptr(), out_bs,
                                                   batch, T, Cin, k, _stream()), "conv1d_cout1")
 
 
-def convtr1d_depthwise(x, x_bs, w, out, out_off, out_bs, batch, T, Cch, stride):
+def convtr1d_depthwise(x, x_bs, x_ts, w, out, out_off, out_bs, out_ts, batch, T, Cch, stride):
     _cuda(x, w, out)
-    _lib.check(_lib.lib().rstnet_convtr1d_depthwise_f32(x.data_ptr(), x_bs, w.data_ptr(), out.data_ptr() + 4 * out_off,
-                                                        out_bs, batch, T, Cch, stride, _stream()), "convtr1d_depthwise")
+    _lib.check(_lib.lib().rstnet_convtr1d_depthwise_f32(x.data_ptr(), x_bs, x_ts, w.data_ptr(), out.data_ptr() + 4 * out_off,
+                                                        out_bs, out_ts, batch, T, Cch, stride, _stream()), "convtr1d_depthwise")
 
 
 def rows_fill(buf, bs, batch, Cch, row0, nrows, mode=0, src_row=0, only_if_zero=None):
@@ -140,30 +140,31 @@ def layer_norm(x, x_off, x_bs, w, b, y, batch, rows, dim, eps):
                                                 batch, rows, dim, eps, _stream()), "layer_norm")
 
 
-def rope_kv_append(qkv, kv, offset, freqs, batch, T, H, D, cap):
+def rope_kv_append(qkv, q_bs, q_ts, kv, offset, freqs, batch, T, H, D, cap):
     _cuda(qkv, kv, offset, freqs)
-    _lib.check(_lib.lib().rstnet_rope_kv_append_f32(qkv.data_ptr(), kv.data_ptr(), offset.data_ptr(), freqs.data_ptr(),
-                                                    batch, T, H, D, cap, _stream()), "rope_kv_append")
+    _lib.check(_lib.lib().rstnet_rope_kv_append_f32(qkv.data_ptr(), q_bs, q_ts, kv.data_ptr(), offset.data_ptr(),
+                                                    freqs.data_ptr(), batch, T, H, D, cap, _stream()), "rope_kv_append")
 
 
-def ring_attention(qkv, kv, offset, out, batch, T, H, D, cap, context, linear):
+def ring_attention(qkv, q_bs, q_ts, kv, offset, out, o_bs, o_ts, batch, T, H, D, cap, context, linear):
     _cuda(qkv, kv, offset, out)
-    _lib.check(_lib.lib().rstnet_ring_attention_f32(qkv.data_ptr(), kv.data_ptr(), offset.data_ptr(), out.data_ptr(),
-                                                    batch, T, H, D, cap, context, int(linear), _stream()), "ring_attention")
+    _lib.check(_lib.lib().rstnet_ring_attention_f32(qkv.data_ptr(), q_bs, q_ts, kv.data_ptr(), offset.data_ptr(),
+                                                    out.data_ptr(), o_bs, o_ts, batch, T, H, D, cap, context, int(linear),
+                                                    _stream()), "ring_attention")
 
 
 def rvq_encode_workspace(N, n_q, dim, bins) -> int:
     return int(_lib.lib().rstnet_rvq_encode_workspace(N, n_q, dim, bins))
 
 
-def rvq_encode(x, ldx, E, Et, enorm, codes, work, N, T, n_q, ns, dim, bins):
+def rvq_encode(x, ldx, E, Et, enorm, codes, work, N, T, n_q, ns, dim, bins, time_major=False):
     _cuda(x, E, Et, enorm, codes, work)
     _lib.check(_lib.lib().rstnet_rvq_encode_f32(x.data_ptr(), ldx, E.data_ptr(), Et.data_ptr(), enorm.data_ptr(),
-                                                codes.data_ptr(), work.data_ptr(), N, T, n_q, ns, dim, bins, _stream()),
-               "rvq_encode")
+                                                codes.data_ptr(), work.data_ptr(), N, T, n_q, ns, dim, bins, int(time_major),
+                                                _stream()), "rvq_encode")
 
 
-def rvq_decode_gather(codes, E, q, N, T, n_q, ns, dim, bins):
+def rvq_decode_gather(codes, E, q, N, T, n_q, ns, dim, bins, time_major=False):
     _cuda(codes, E, q)
     _lib.check(_lib.lib().rstnet_rvq_decode_gather_f32(codes.data_ptr(), E.data_ptr(), q.data_ptr(), N, T, n_q, ns, dim,
-                                                       bins, _stream()), "rvq_decode_gather")
+                                                       bins, int(time_major), _stream()), "rvq_decode_gather")

@@ -115,7 +115,7 @@ def test_conv_cin1_cout1_depthwise():
     xin = torch.zeros(B, 6 + T, device=DEV)
     xin[:, 6:] = x[:, 0].to(DEV)
     out = torch.empty(B, T, 64, device=DEV)
-    ops.conv1d_cin1(xin, 6 + T, w.reshape(64, 7).contiguous().to(DEV), b.to(DEV), out, 0, T * 64, B, T, 64, 7)
+    ops.conv1d_cin1(xin, 6 + T, 1, w.reshape(64, 7).contiguous().to(DEV), b.to(DEV), out, 0, T * 64, 64, B, T, 64, 7)
     assert _maxdiff(out.permute(0, 2, 1), ref) <= 1e-5
     # Cout == 1, k3
     x2 = torch.randn(B, 64, T, generator=g)
@@ -125,7 +125,7 @@ def test_conv_cin1_cout1_depthwise():
     buf = torch.zeros(B, 2 + T, 64, device=DEV)
     buf[:, 2:] = x2.permute(0, 2, 1).to(DEV)
     out2 = torch.empty(B, T, device=DEV)
-    ops.conv1d_cout1(buf, (2 + T) * 64, w2[0].t().contiguous().reshape(-1).to(DEV), b2.to(DEV), out2, T, B, T, 64, 3)
+    ops.conv1d_cout1(buf, (2 + T) * 64, 64, w2[0].t().contiguous().reshape(-1).to(DEV), b2.to(DEV), out2, T, B, T, 64, 3)
     assert _maxdiff(out2, ref2[:, 0]) <= 1e-5
     # depthwise transposed conv k4 s2
     x3 = torch.randn(B, 512, 50, generator=g)
@@ -134,7 +134,7 @@ def test_conv_cin1_cout1_depthwise():
     buf3 = torch.zeros(B, 51, 512, device=DEV)
     buf3[:, 1:] = x3.permute(0, 2, 1).to(DEV)
     out3 = torch.empty(B, 100, 512, device=DEV)
-    ops.convtr1d_depthwise(buf3, 51 * 512, w3.reshape(512, 4).contiguous().to(DEV), out3, 0, 100 * 512, B, 50, 512, 2)
+    ops.convtr1d_depthwise(buf3, 51 * 512, 512, w3.reshape(512, 4).contiguous().to(DEV), out3, 0, 100 * 512, 512, B, 50, 512, 2)
     assert _maxdiff(out3.permute(0, 2, 1), ref3) <= 1e-5
 
 
@@ -175,8 +175,8 @@ def test_rope_ring_attention_vs_oracle(T, steps, cap, context):
         ref = F.scaled_dot_product_attention(q, kk, vv, bias).permute(0, 2, 1, 3).reshape(B, T, H * D)
         qd = qkv.to(DEV).contiguous()
         out = torch.empty(B, T, H * D, device=DEV)
-        ops.rope_kv_append(qd, kv, offset, freqs, B, T, H, D, cap)
-        ops.ring_attention(qd, kv, offset, out, B, T, H, D, cap, context, ring is None)
+        ops.rope_kv_append(qd, T * 3 * H * D, 3 * H * D, kv, offset, freqs, B, T, H, D, cap)
+        ops.ring_attention(qd, T * 3 * H * D, 3 * H * D, kv, offset, out, T * H * D, H * D, B, T, H, D, cap, context, ring is None)
         ops.counter_add(offset, T)
         off += T
         if step in (0, steps // 2, steps - 1):
@@ -252,7 +252,7 @@ def test_cfg1_encode_decode_vs_reference_golden(golden_dir, codec):
     g = np.load(os.path.join(golden_dir, "mimi_cfg1.npz"))
     x = S.synthetic_audio(1, 24000, seed=int(g["audio_seed"])).to(DEV)
     codes = codec.encode(x)
-    plan = codec._engine.enc_plan(1, 24000, False)
+    plan = codec._engine.enc_plan(1, 24000)
     lat = plan.lat.view(1, 13, 512).permute(0, 2, 1)
     d_lat = _maxdiff(lat, torch.from_numpy(g["z_lat"]))
     print(f"latent max|d| vs reference = {d_lat:.3e}")
@@ -289,12 +289,14 @@ def test_empty_input(codec):
     assert codec.decode(torch.zeros(2, 8, 0, dtype=torch.int64, device=DEV)).shape == (2, 1, 0)
 
 
-@pytest.mark.parametrize("graphs", [False, True])
-def test_streaming_vs_reference_golden_and_batch(golden_dir, codec, graphs):
-    """MimiModel streaming (compression.py:368-423) golden + the reference property streaming == batch."""
+@pytest.mark.parametrize("graphs,tc", [(False, False), (True, False), (False, True), (True, True)])
+def test_streaming_vs_reference_golden_and_batch(golden_dir, codec, graphs, tc):
+    """MimiModel streaming (compression.py:368-423) golden + the reference property streaming == batch.
+    tc=False: fp32 FFMA kernels (same arithmetic as the batch path -> identical results);
+    tc=True: tcgen05 3xTF32 GEMMs (fp32-equivalent; indices may differ only on near-ties)."""
     g = np.load(os.path.join(golden_dir, "mimi_stream6.npz"))
     x = S.synthetic_audio(2, 1920 * 6, seed=int(g["audio_seed"])).to(DEV)
-    codec.use_cuda_graphs = graphs
+    codec.use_cuda_graphs, codec.streaming_tensor_cores = graphs, tc
     cs, ws = [], []
     with codec.streaming(2):
         for i in range(6):
@@ -305,19 +307,25 @@ def test_streaming_vs_reference_golden_and_batch(golden_dir, codec, graphs):
     codes, wav = torch.cat(cs, -1), torch.cat(ws, -1)
     b_codes = codec.encode(x)
     b_wav = codec.decode(torch.from_numpy(g["codes"]).to(DEV))
-    # our streaming and batch paths run the same kernels row for row: identical results
-    assert torch.equal(codes, b_codes)
-    assert _maxdiff(wav, b_wav) == 0.0
-    assert _maxdiff(wav, torch.from_numpy(g["wav"])) <= 1e-4 * max(1.0, float(np.abs(g["wav"]).max()))
+    peak = max(1.0, float(np.abs(g["wav"]).max()))
+    if not tc:
+        # streaming and batch run the same kernels row for row: identical results
+        assert torch.equal(codes, b_codes)
+        assert _maxdiff(wav, b_wav) == 0.0
+    else:
+        assert (codes != b_codes).any(dim=1).float().mean().item() <= 0.1
+        assert _maxdiff(wav, b_wav) <= 1e-4 * peak
+    d = _maxdiff(wav, torch.from_numpy(g["wav"]))
     bad = (codes.cpu() != torch.from_numpy(g["codes"])).any(dim=1)
-    print(f"streaming frames with index mismatch vs reference: {int(bad.sum())}/12")
+    print(f"tc={tc} graphs={graphs}: wav max|d| vs reference {d:.2e}; frames with index mismatch {int(bad.sum())}/12")
+    assert d <= 1e-4 * peak
     assert bad.float().mean().item() <= 0.1
 
 
 def test_streaming_reset_and_causality(codec):
     """reset_streaming (streaming.py:115-126) restarts the stream; outputs never depend on the future."""
     x = S.synthetic_audio(3, 1920 * 3, seed=21).to(DEV)
-    codec.use_cuda_graphs = True
+    codec.use_cuda_graphs, codec.streaming_tensor_cores = True, True
     with codec.streaming(3):
         first = [codec.encode(x[..., i * 1920:(i + 1) * 1920]) for i in range(3)]
         codec.reset_streaming()
@@ -329,11 +337,12 @@ def test_streaming_reset_and_causality(codec):
     assert torch.equal(full[..., :2], prefix)
 
 
-def test_cfg2_shape_properties_full_batch(codec):
+@pytest.mark.parametrize("tc", [False, True])
+def test_cfg2_shape_properties_full_batch(codec, tc):
     """BASELINE configs[1] size (B=256 streams): encode -> decode -> shapes, finiteness, determinism."""
     B = 256
     x = S.synthetic_audio(4, 1920 * 2, seed=33).repeat(B // 4, 1, 1).to(DEV)
-    codec.use_cuda_graphs = True
+    codec.use_cuda_graphs, codec.streaming_tensor_cores = True, tc
     with codec.streaming(B):
         outs = []
         for i in range(2):
@@ -345,4 +354,8 @@ def test_cfg2_shape_properties_full_batch(codec):
     assert torch.isfinite(wav).all() and int(codes.min()) >= 0 and int(codes.max()) < 2048
     # identical streams give identical tokens (batch rows are independent)
     assert torch.equal(codes[:4], codes[4:8]) and torch.equal(wav[:4], wav[252:256])
-    assert torch.equal(codes[:4], codec.encode(x[:4]))
+    ref = codec.encode(x[:4])
+    if tc:
+        assert (codes[:4] != ref).any(dim=1).float().mean().item() <= 0.25
+    else:
+        assert torch.equal(codes[:4], ref)
