@@ -69,7 +69,8 @@ int rstnet_gemm_rows_f32(const rstnet_gemm_rows_args* args, rstnet_stream_t stre
  * C + o*c_o_stride + i*c_i_stride + n, or, when n_split > 0 (transposed conv: n = j*n_split + co),
  * to C + o*c_o_stride + i*c_i_stride + j*c_split_stride + co; R (optional residual) likewise.
  * Epilogue: post(R + scale*(acc + bias)); pre_act is applied to A in shared memory.
- * precision 0 = 3xTF32 split (fp32-equivalent, for RVQ-index exactness), 1 = single TF32 pass.
+ * precision 0 = 3xTF32 split (fp32-equivalent, for RVQ-index exactness; W must already be rounded to
+ * TF32 and W_lo = tf32(w - W) supplied -- see rstnet_tf32_split_f32), 1 = single TF32 pass.
  * Same reference call sites as rstnet_gemm_rows_f32. */
 typedef struct rstnet_tc_plan rstnet_tc_plan;
 typedef struct {
@@ -78,6 +79,7 @@ typedef struct {
   int32_t a_c_extent, a_i_extent, a_o_extent;
   int32_t taps, tap_di, tap_do, o_mul;
   const float* W;
+  const float* W_lo;
   int32_t N, Kc;
   int32_t I_out, O_out;
   float* C;
@@ -88,17 +90,26 @@ typedef struct {
   const float* scale;
   int32_t n_split;
   int32_t pre_act, post_act, precision;
+  float* C2;    /* optional second output act2(R + scale*(acc + bias)) written with C's strides */
+  int32_t act2;
 } rstnet_tc_gemm_desc;
 int rstnet_tc_gemm_create(const rstnet_tc_gemm_desc* desc, rstnet_tc_plan** out);
 int rstnet_tc_gemm_run(const rstnet_tc_plan* plan, rstnet_stream_t stream);
 void rstnet_tc_gemm_destroy(rstnet_tc_plan* plan);
+/* profiling aid: CTA (0,0) writes clock64 stamps per k iteration to trace[taps*Kc/32][8]
+ * (0 producer, 1 operands landed, 2 transformed, 3 MMA start, 4 MMA issued, 5/6 drain begin/end) */
+void rstnet_tc_gemm_set_trace(rstnet_tc_plan* plan, int64_t* trace, int64_t* cta_times /* [grid.x][4] globaltimer ns */);
+int rstnet_tc_gemm_grid(const rstnet_tc_plan* plan, int32_t* grid_x, int32_t* grid_y, int32_t* tile_n);
+/* hi[i] = tf32_rna(x[i]); lo[i] = tf32_rna(x[i] - hi[i])  (one-time weight preparation for precision 0) */
+int rstnet_tf32_split_f32(const float* x, float* hi, float* lo, int64_t n, rstnet_stream_t stream);
 
 /* ---- first SEANet encoder conv, Cin == 1 (modules/seanet.py:177-187): sample (b, t) at
  * x + b*x_batch_stride + t*x_time_stride (padded, T + k - 1 samples per stream), w [Cout][k],
  * out rows at out + b*out_batch_stride + t*out_time_stride. */
 int rstnet_conv1d_cin1_f32(const float* x, int64_t x_batch_stride, int64_t x_time_stride, const float* w, const float* bias,
-                           float* out, int64_t out_batch_stride, int64_t out_time_stride, int32_t batch,
-                           int32_t T, int32_t Cout, int32_t k, int32_t post_act, rstnet_stream_t stream);
+                           float* out, float* out2 /* optional act2 copy, same strides */, int64_t out_batch_stride,
+                           int64_t out_time_stride, int32_t batch, int32_t T, int32_t Cout, int32_t k,
+                           int32_t post_act, int32_t act2, rstnet_stream_t stream);
 
 /* ---- last SEANet decoder conv, Cout == 1 (modules/seanet.py:372-384): x row (b, t) =
  * Cin floats at x + b*x_batch_stride + t*x_time_stride (padded, already activated),

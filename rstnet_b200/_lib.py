@@ -16,7 +16,7 @@ ACT_NONE, ACT_ELU, ACT_GELU = 0, 1, 2
 # every symbol include/rstnet_b200.h declares (tests assert the .so exports all of them)
 SYMBOLS = [
     "rstnet_version", "rstnet_last_error", "rstnet_launch_count",
-    "rstnet_gemm_rows_f32", "rstnet_tc_gemm_create", "rstnet_tc_gemm_run", "rstnet_tc_gemm_destroy", "rstnet_conv1d_cin1_f32", "rstnet_conv1d_cout1_f32",
+    "rstnet_gemm_rows_f32", "rstnet_tc_gemm_create", "rstnet_tc_gemm_run", "rstnet_tc_gemm_destroy", "rstnet_tc_gemm_set_trace", "rstnet_tc_gemm_grid", "rstnet_tf32_split_f32", "rstnet_conv1d_cin1_f32", "rstnet_conv1d_cout1_f32",
     "rstnet_convtr1d_depthwise_f32", "rstnet_rows_fill_f32", "rstnet_rows_copy_table_f32",
     "rstnet_counter_add", "rstnet_layer_norm_f32", "rstnet_rope_kv_append_f32",
     "rstnet_ring_attention_f32", "rstnet_rvq_encode_workspace", "rstnet_rvq_encode_f32",
@@ -40,11 +40,12 @@ class TcGemmDesc(C.Structure):
         ("A", C.c_void_p), ("a_i_stride", C.c_int64), ("a_o_stride", C.c_int64),
         ("a_c_extent", C.c_int32), ("a_i_extent", C.c_int32), ("a_o_extent", C.c_int32),
         ("taps", C.c_int32), ("tap_di", C.c_int32), ("tap_do", C.c_int32), ("o_mul", C.c_int32),
-        ("W", C.c_void_p), ("N", C.c_int32), ("Kc", C.c_int32), ("I_out", C.c_int32), ("O_out", C.c_int32),
+        ("W", C.c_void_p), ("W_lo", C.c_void_p), ("N", C.c_int32), ("Kc", C.c_int32), ("I_out", C.c_int32), ("O_out", C.c_int32),
         ("C", C.c_void_p), ("c_i_stride", C.c_int64), ("c_o_stride", C.c_int64), ("c_split_stride", C.c_int64),
         ("R", C.c_void_p), ("r_i_stride", C.c_int64), ("r_o_stride", C.c_int64), ("r_split_stride", C.c_int64),
         ("bias", C.c_void_p), ("scale", C.c_void_p),
         ("n_split", C.c_int32), ("pre_act", C.c_int32), ("post_act", C.c_int32), ("precision", C.c_int32),
+        ("C2", C.c_void_p), ("act2", C.c_int32),
     ]
 
 
@@ -79,7 +80,11 @@ def lib() -> C.CDLL:
     L.rstnet_tc_gemm_run.argtypes = [vp, vp]
     L.rstnet_tc_gemm_destroy.argtypes = [vp]
     L.rstnet_tc_gemm_destroy.restype = None
-    L.rstnet_conv1d_cin1_f32.argtypes = [vp, i64, i64, vp, vp, vp, i64, i64, i32, i32, i32, i32, i32, vp]
+    L.rstnet_tc_gemm_set_trace.argtypes = [vp, vp, vp]
+    L.rstnet_tc_gemm_grid.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.rstnet_tc_gemm_set_trace.restype = None
+    L.rstnet_tf32_split_f32.argtypes = [vp, vp, vp, i64, vp]
+    L.rstnet_conv1d_cin1_f32.argtypes = [vp, i64, i64, vp, vp, vp, vp, i64, i64, i32, i32, i32, i32, i32, i32, vp]
     L.rstnet_conv1d_cout1_f32.argtypes = [vp, i64, i64, vp, vp, vp, i64, i32, i32, i32, i32, vp]
     L.rstnet_convtr1d_depthwise_f32.argtypes = [vp, i64, i64, vp, vp, i64, i64, i32, i32, i32, i32, vp]
     L.rstnet_rows_fill_f32.argtypes = [vp, i64, i32, i32, i32, i32, i32, i32, vp, vp]

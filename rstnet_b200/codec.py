@@ -467,6 +467,13 @@ class _Plan:
     def buf(self, ctx, T, extra, C) -> _Buf:
         return _Buf(self.B, ctx, T, extra, C, self.eng.device, self.tc)
 
+    @staticmethod
+    def tc_weights(pack):
+        """TF32 (hi, lo) split of a weight pack, computed once and cached on the pack."""
+        if "W_hi" not in pack:
+            pack["W_hi"], pack["W_lo"] = ops.tf32_split(pack["W"])
+        return pack["W_hi"], pack["W_lo"]
+
     def add(self, fn):
         self.ops_list.append(fn)
 
@@ -476,7 +483,10 @@ class _Plan:
 
     # ---- conv / transposed conv over a _Buf (taps along time)
     def conv(self, A: _Buf, a_row0: int, stride: int, pack, out: _Buf, out_row0: int, T_out: int, *, pre=ACT_NONE,
-             post=ACT_NONE, R: Optional[_Buf] = None, r_row0: int = 0, tr_stride: int = 0):
+             post=ACT_NONE, R: Optional[_Buf] = None, r_row0: int = 0, tr_stride: int = 0, out2: Optional[_Buf] = None,
+             out2_row0: int = 0):
+        """out2 (tensor-core plans only): ELU'd copy of the raw output, written by the same epilogue, so the
+        consumer that needs a pre-activation (resblock conv1) does not re-apply ELU per tap and per N tile."""
         B, Cin = self.B, A.C
         taps = pack["taps"]
         N = pack["W"].shape[0]
@@ -492,8 +502,11 @@ class _Plan:
             kw.update(R=R.t, r_off=R.off(r_row0), r_i_stride=R.C, r_o_stride=B * R.C)
         if tr_stride:
             kw.update(n_split=out.C, c_split_stride=B * out.C)
-        plan = ops.TcGemm(A.t, A.off(a_row0), Cin, B * Cin, Cin, B, A.rows - a_row0, pack["W"], Cin, out.t, out.off(out_row0),
-                          out.C, (tr_stride or 1) * B * out.C, B, T_out, **kw)
+        if out2 is not None:
+            kw.update(C2=out2.t, c2_off=out2.off(out2_row0), act2=ACT_ELU)
+        w_hi, w_lo = self.tc_weights(pack)
+        plan = ops.TcGemm(A.t, A.off(a_row0), Cin, B * Cin, Cin, B, A.rows - a_row0, w_hi, Cin, out.t, out.off(out_row0),
+                          out.C, (tr_stride or 1) * B * out.C, B, T_out, W_lo=w_lo, **kw)
         self.add(plan.run)
 
     # ---- linear over `rows` consecutive rows
@@ -511,7 +524,9 @@ class _Plan:
         kw = dict(post_act=post, scale=scale, precision=self.precision)
         if R_view is not None:
             kw.update(R=out_t, r_off=R_view[0], r_i_stride=N_row_stride, r_o_stride=rpb * N_row_stride)
-        plan = ops.TcGemm(A_t, a_off, K, rpb * K, K, rpb, 1, pack["W"], K, out_t, c_off, N_row_stride, rpb * N_row_stride, rpb, 1, **kw)
+        w_hi, w_lo = self.tc_weights(pack)
+        plan = ops.TcGemm(A_t, a_off, K, rpb * K, K, rpb, 1, w_hi, K, out_t, c_off, N_row_stride, rpb * N_row_stride, rpb, 1,
+                          W_lo=w_lo, **kw)
         self.add(plan.run)
 
     def rows_view(self, X: _Buf, row0: int, nrows: int):
@@ -603,10 +618,11 @@ class _EncPlan(_Plan):
         s = m.resample_stride
         self.T5 = T5 = _ceil_div(F, s)
         self.xin = xin = self.buf(k0 - 1, L, 0, 1)
-        y, h, r_ = [], [], []
+        y, ya, h, r_ = [], [], [], []  # ya: ELU'd copies feeding the resblocks' first conv (tensor-core plans)
         C = nf
         for i, ratio in enumerate(eng.enc_ratios):
-            y.append(self.buf(m.residual_kernel_size - 1, T[i], 0, C))
+            y.append(self.buf(0 if self.tc else m.residual_kernel_size - 1, T[i], 0, C))
+            ya.append(self.buf(m.residual_kernel_size - 1, T[i], 0, C) if self.tc else y[-1])
             h.append(self.buf(0, T[i], 0, C // m.compress))
             r_.append(self.buf(ratio, T[i], T[i + 1] * ratio - T[i], C))
             C *= 2
@@ -620,15 +636,23 @@ class _EncPlan(_Plan):
         self._keep = (xproj, work)
 
         # conv0: 1 -> nf, k7 (HBM-bound, CUDA cores)
-        self.add(lambda: ops.conv1d_cin1(xin.t, xin.bs, xin.ts, eng.e_conv0_w, eng.e_conv0_b, y[0].t, y[0].off(y[0].ctx),
-                                         y[0].bs, y[0].ts, B, L, nf, k0, ACT_NONE))
+        if self.tc:
+            self.add(lambda: ops.conv1d_cin1(xin.t, xin.bs, xin.ts, eng.e_conv0_w, eng.e_conv0_b, y[0].t, 0, y[0].bs, y[0].ts, B, L,
+                                             nf, k0, ACT_NONE, out2=ya[0].t, out2_off=ya[0].off(ya[0].ctx), act2=ACT_ELU))
+        else:
+            self.add(lambda: ops.conv1d_cin1(xin.t, xin.bs, xin.ts, eng.e_conv0_w, eng.e_conv0_b, y[0].t, y[0].off(y[0].ctx),
+                                             y[0].bs, y[0].ts, B, L, nf, k0, ACT_NONE))
         for i, ratio in enumerate(eng.enc_ratios):
             w1, w2 = eng.e_res[i]
             # SEANetResnetBlock: ELU -> k3 -> ELU -> k1, + skip; the ELU that follows is fused as post_act
-            self.conv(y[i], 0, 1, w1, h[i], 0, T[i], pre=ACT_ELU, post=ACT_ELU)
+            self.conv(ya[i], 0, 1, w1, h[i], 0, T[i], pre=ACT_NONE if self.tc else ACT_ELU, post=ACT_ELU)
             self.conv(h[i], 0, 1, w2, r_[i], r_[i].ctx, T[i], post=ACT_ELU, R=y[i], r_row0=y[i].ctx)
-            nxt = y[i + 1] if i + 1 < len(y) else y4
-            self.conv(r_[i], 0, ratio, eng.e_down[i], nxt, nxt.ctx, T[i + 1], post=ACT_NONE if nxt is not y4 else ACT_ELU)
+            if i + 1 < len(y):
+                nxt = y[i + 1]
+                self.conv(r_[i], 0, ratio, eng.e_down[i], nxt, nxt.ctx, T[i + 1],
+                          out2=ya[i + 1] if self.tc else None, out2_row0=ya[i + 1].ctx)
+            else:
+                self.conv(r_[i], 0, ratio, eng.e_down[i], y4, y4.ctx, T[i + 1], post=ACT_ELU)
         self.conv(y4, 0, 1, eng.e_final, X, X.ctx, F)
         self.transformer("encoder_transformer", X, X.ctx, F)
         # ConvDownsample1d: replicate padding (left on the first call only when streaming)
@@ -642,7 +666,7 @@ class _EncPlan(_Plan):
         self.linear(lat, self.flat_view(T5, D), D, eng.q_in, xproj, self.flat_view(T5, 2 * cd), 2 * cd)
         self.add(lambda: ops.rvq_encode(xproj, 2 * cd, eng.E, eng.Et, eng.enorm, codes, work, B * T5, T5, m.n_q, m.n_q_semantic,
                                         cd, m.codebook_size, time_major=self.tc))
-        self.finish_streaming([xin] + y + r_ + [y4, X], F)
+        self.finish_streaming([xin] + (ya if self.tc else y) + r_ + [y4, X], F)
 
     def run(self, x: torch.Tensor, graphs: Optional[bool]) -> torch.Tensor:
         xin, L = self.xin, self.L
@@ -683,11 +707,12 @@ class _DecPlan(_Plan):
         X = self.buf(m.kernel_size - 1, F, 0, D)
         C = nf * 2 ** len(eng.ratios)
         a = [self.buf(1, F, 0, C)]
-        yd, hd_ = [], []
+        yd, yda, hd_ = [], [], []
         Tin = F
         for i, r in enumerate(eng.ratios):
             Tout = Tin * r
-            yd.append(self.buf(m.residual_kernel_size - 1, Tout, 0, C // 2))
+            yd.append(self.buf(0 if self.tc else m.residual_kernel_size - 1, Tout, 0, C // 2))
+            yda.append(self.buf(m.residual_kernel_size - 1, Tout, 0, C // 2) if self.tc else yd[-1])
             hd_.append(self.buf(0, Tout, 0, C // 2 // m.compress))
             last = i == len(eng.ratios) - 1
             a.append(self.buf((m.last_kernel_size - 1) if last else 1, Tout, 0, C // 2))
@@ -705,16 +730,17 @@ class _DecPlan(_Plan):
         Tin = F
         for i, r in enumerate(eng.ratios):
             # ConvTranspose1d k=2r stride r as a 2-tap GEMM over [x[t-1], x[t]]: one output row = r time steps
-            self.conv(a[i], 0, 1, eng.d_tr[i], yd[i], yd[i].ctx, Tin, tr_stride=r)
+            self.conv(a[i], 0, 1, eng.d_tr[i], yd[i], yd[i].ctx, Tin, tr_stride=r, out2=yda[i] if self.tc else None,
+                      out2_row0=yda[i].ctx)
             Tout = Tin * r
             w1, w2 = eng.d_res[i]
-            self.conv(yd[i], 0, 1, w1, hd_[i], 0, Tout, pre=ACT_ELU, post=ACT_ELU)
+            self.conv(yda[i], 0, 1, w1, hd_[i], 0, Tout, pre=ACT_NONE if self.tc else ACT_ELU, post=ACT_ELU)
             self.conv(hd_[i], 0, 1, w2, a[i + 1], a[i + 1].ctx, Tout, post=ACT_ELU, R=yd[i], r_row0=yd[i].ctx)
             Tin = Tout
         last = a[-1]
         self.add(lambda: ops.conv1d_cout1(last.t, last.bs, last.ts, eng.d_final_w, eng.d_final_b, wav, Lout, B, Lout, last.C,
                                           m.last_kernel_size))
-        self.finish_streaming([qup, X] + a + yd, F)
+        self.finish_streaming([qup, X] + a + (yda if self.tc else yd), F)
 
     def run(self, codes: torch.Tensor, graphs: Optional[bool]) -> torch.Tensor:
         self.codes_in.copy_(codes)

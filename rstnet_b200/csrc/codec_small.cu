@@ -10,8 +10,8 @@ extern void count_launch();
 // block = (Cout threads in x) x (TT time steps in y-loop); x window staged in smem.
 template <int TT>
 __global__ void conv_cin1_kernel(const float* __restrict__ x, long long xbs, long long xts, const float* __restrict__ w,
-                                 const float* __restrict__ bias, float* __restrict__ out, long long obs, long long ots,
-                                 int T, int Cout, int k, int post_act) {
+                                 const float* __restrict__ bias, float* __restrict__ out, float* __restrict__ out2,
+                                 long long obs, long long ots, int T, int Cout, int k, int post_act, int act2) {
   extern __shared__ float xs[];  // TT + k - 1
   const int b = blockIdx.y;
   const long long t0 = (long long)blockIdx.x * TT;
@@ -32,6 +32,7 @@ __global__ void conv_cin1_kernel(const float* __restrict__ x, long long xbs, lon
       for (int j = 0; j < 16; ++j)
         if (j < k) acc = fmaf(xs[t + j], wr[j], acc);
       acc += bv;
+      if (out2) out2[(long long)b * obs + (t0 + t) * ots + co] = apply_act(acc, act2);
       out[(long long)b * obs + (t0 + t) * ots + co] = apply_act(acc, post_act);
     }
   }
@@ -144,15 +145,15 @@ __global__ void layer_norm_kernel(const float* __restrict__ x, long long xbs, co
 using namespace rstnet;
 
 extern "C" int rstnet_conv1d_cin1_f32(const float* x, int64_t xbs, int64_t xts, const float* w, const float* bias, float* out,
-                                      int64_t obs, int64_t ots, int32_t batch, int32_t T, int32_t Cout, int32_t k,
-                                      int32_t post_act, rstnet_stream_t stream) {
+                                      float* out2, int64_t obs, int64_t ots, int32_t batch, int32_t T, int32_t Cout,
+                                      int32_t k, int32_t post_act, int32_t act2, rstnet_stream_t stream) {
   RSTNET_REQUIRE(x && w && out, "conv1d_cin1: null pointer");
   RSTNET_REQUIRE(batch > 0 && T > 0 && Cout > 0 && k > 0 && k <= 16, "conv1d_cin1: bad shape (k<=16 required, k=%d)", k);
   constexpr int TT = 128;
   dim3 grid((unsigned)ceil_div(T, TT), (unsigned)batch);
   const int threads = Cout >= 128 ? 128 : (Cout >= 64 ? 64 : 32);
   conv_cin1_kernel<TT><<<grid, threads, (TT + k - 1) * sizeof(float), (cudaStream_t)stream>>>(
-      x, xbs, xts, w, bias, out, obs, ots, T, Cout, k, post_act);
+      x, xbs, xts, w, bias, out, out2, obs, ots, T, Cout, k, post_act, act2);
   count_launch();
   return check_launch("conv1d_cin1");
 }
@@ -205,7 +206,8 @@ extern "C" int rstnet_rows_copy_table_f32(const rstnet_row_copy* table_dev, int3
   RSTNET_REQUIRE(table_dev, "rows_copy_table: null pointer");
   if (n_entries <= 0 || batch <= 0) return 0;
   RSTNET_REQUIRE(n_entries <= 65535 && batch <= 65535, "rows_copy_table: too many entries / batch");
-  rows_copy_table_kernel<<<dim3(4, n_entries, batch), 256, 0, (cudaStream_t)stream>>>(table_dev, n_entries);
+  // grid.x strides over the channel columns of an entry (up to batch*C in the time-major layout)
+  rows_copy_table_kernel<<<dim3(batch > 1 ? 4 : 256, n_entries, batch), 256, 0, (cudaStream_t)stream>>>(table_dev, n_entries);
   count_launch();
   return check_launch("rows_copy_table");
 }

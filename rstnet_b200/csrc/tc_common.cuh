@@ -11,6 +11,18 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
+// one elected lane of a fully converged warp; keeps the surrounding control flow warp-uniform so
+// that ptxas feeds tcgen05 / TMA operands from uniform registers without per-instruction waterfall loops
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

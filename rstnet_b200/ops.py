@@ -49,6 +49,15 @@ def gemm_rows(A: torch.Tensor, a_off: int, a_bs: int, a_rs: int, Wt: torch.Tenso
     _lib.check(_lib.lib().rstnet_gemm_rows_f32(C.byref(a), _stream()), "gemm_rows_f32")
 
 
+def tf32_split(w: torch.Tensor):
+    """(hi, lo) with hi = tf32_rna(w), lo = tf32_rna(w - hi): one-time weight preparation for 3xTF32."""
+    _cuda(w)
+    w = w.contiguous()
+    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    _lib.check(_lib.lib().rstnet_tf32_split_f32(w.data_ptr(), hi.data_ptr(), lo.data_ptr(), w.numel(), _stream()), "tf32_split")
+    return hi, lo
+
+
 class TcGemm:
     """A tcgen05 GEMM plan bound to fixed buffers (rstnet_tc_gemm_create / run / destroy).
 
@@ -58,23 +67,28 @@ class TcGemm:
     def __init__(self, A, a_off, a_i_stride, a_o_stride, a_c_extent, a_i_extent, a_o_extent, W, Kc, C_, c_off, c_i_stride,
                  c_o_stride, I_out, O_out, *, taps=1, tap_di=0, tap_do=0, o_mul=1, bias=None, scale=None, R=None, r_off=0,
                  r_i_stride=0, r_o_stride=0, n_split=0, c_split_stride=0, r_split_stride=0, pre_act=ACT_NONE,
-                 post_act=ACT_NONE, precision=0):
-        _cuda(A, W, C_, bias, scale, R)
+                 post_act=ACT_NONE, precision=0, W_lo=None, C2=None, c2_off=0, act2=ACT_NONE):
+        _cuda(A, W, C_, bias, scale, R, W_lo)
         N, Ktot = W.shape
+        if precision == 0 and W_lo is None:
+            W, W_lo = tf32_split(W)
         assert Ktot == taps * Kc, (Ktot, taps, Kc)
         d = TcGemmDesc()
         d.A = A.data_ptr() + 4 * a_off
         d.a_i_stride, d.a_o_stride = a_i_stride, a_o_stride
         d.a_c_extent, d.a_i_extent, d.a_o_extent = a_c_extent, a_i_extent, a_o_extent
         d.taps, d.tap_di, d.tap_do, d.o_mul = taps, tap_di, tap_do, o_mul
-        d.W, d.N, d.Kc, d.I_out, d.O_out = W.data_ptr(), N, Kc, I_out, O_out
+        d.W, d.W_lo, d.N, d.Kc, d.I_out, d.O_out = W.data_ptr(), _p(W_lo), N, Kc, I_out, O_out
         d.C = C_.data_ptr() + 4 * c_off
         d.c_i_stride, d.c_o_stride, d.c_split_stride = c_i_stride, c_o_stride, c_split_stride
         d.R = None if R is None else R.data_ptr() + 4 * r_off
         d.r_i_stride, d.r_o_stride, d.r_split_stride = r_i_stride, r_o_stride, r_split_stride
         d.bias, d.scale = _p(bias), _p(scale)
         d.n_split, d.pre_act, d.post_act, d.precision = n_split, pre_act, post_act, precision
-        self._keep = (A, W, C_, bias, scale, R)  # the plan embeds raw pointers
+        d.C2 = None if C2 is None else C2.data_ptr() + 4 * c2_off
+        d.act2 = act2
+        self._keep = (A, W, W_lo, C_, bias, scale, R, C2)  # the plan embeds raw pointers
+        self.flops = 2.0 * I_out * O_out * N * Ktot  # algorithmic (one fp32-equivalent product per MAC)
         self._h = C.c_void_p()
         _lib.check(_lib.lib().rstnet_tc_gemm_create(C.byref(d), C.byref(self._h)), "tc_gemm_create")
 
@@ -91,10 +105,12 @@ class TcGemm:
             self._h = None
 
 
-def conv1d_cin1(x, x_bs, x_ts, w, bias, out, out_off, out_bs, out_ts, batch, T, Cout, k, post_act=ACT_NONE):
-    _cuda(x, w, out)
+def conv1d_cin1(x, x_bs, x_ts, w, bias, out, out_off, out_bs, out_ts, batch, T, Cout, k, post_act=ACT_NONE, out2=None,
+                out2_off=0, act2=ACT_NONE):
+    _cuda(x, w, out, out2)
     _lib.check(_lib.lib().rstnet_conv1d_cin1_f32(x.data_ptr(), x_bs, x_ts, w.data_ptr(), _p(bias), out.data_ptr() + 4 * out_off,
-                                                 out_bs, out_ts, batch, T, Cout, k, post_act, _stream()), "conv1d_cin1")
+                                                 None if out2 is None else out2.data_ptr() + 4 * out2_off, out_bs, out_ts,
+                                                 batch, T, Cout, k, post_act, act2, _stream()), "conv1d_cin1")
 
 
 def conv1d_cout1(x, x_bs, x_ts, w, bias, out, out_bs, batch, T, Cin, k):

@@ -115,7 +115,10 @@ def test_conv_cin1_cout1_depthwise():
     xin = torch.zeros(B, 6 + T, device=DEV)
     xin[:, 6:] = x[:, 0].to(DEV)
     out = torch.empty(B, T, 64, device=DEV)
-    ops.conv1d_cin1(xin, 6 + T, 1, w.reshape(64, 7).contiguous().to(DEV), b.to(DEV), out, 0, T * 64, 64, B, T, 64, 7)
+    out2 = torch.empty_like(out)
+    ops.conv1d_cin1(xin, 6 + T, 1, w.reshape(64, 7).contiguous().to(DEV), b.to(DEV), out, 0, T * 64, 64, B, T, 64, 7,
+                    out2=out2, act2=ACT_ELU)
+    assert _maxdiff(out2.permute(0, 2, 1), F.elu(ref)) <= 1e-5
     assert _maxdiff(out.permute(0, 2, 1), ref) <= 1e-5
     # Cout == 1, k3
     x2 = torch.randn(B, 64, T, generator=g)
