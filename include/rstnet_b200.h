@@ -189,6 +189,60 @@ int rstnet_rvq_decode_gather_f32(const int64_t* codes, const float* E, float* q,
                                  int32_t n_q, int32_t n_q_semantic, int32_t dim, int32_t bins,
                                  int32_t time_major, rstnet_stream_t stream);
 
+/* ======================================================================================
+ * Speech-text LM decode step (MLLM_v2/models/llama_streaming.py GPT under `with gpt.streaming(B)`),
+ * bf16 activations / weights, fp32 accumulation.  One token per stream: rows are streams.
+ * ====================================================================================== */
+
+/* ---- weight-streaming GEMM  out[m,n] = sum_k X[m,k] * W[n,k] (+ R[m,n]), all bf16, W exactly as
+ * nn.Linear stores it.  tcgen05 (kind::f16) with W as the 128-row MMA operand, TMA-staged, fp32
+ * accumulator in TMEM, optional split-K (fp32 partials in `partial_ws` + finalize).  Replaces F.linear
+ * in LoRAQKVLinear/LoRALinear after merge (llama_streaming.py:113-143, 368-406), LLaMAMLP
+ * (lit_model.py:399-403), lm_head (:691), codecformer_in / multi_linear / gating / audio_linears
+ * (llama_streaming.py:727-749, modules/transformer.py:155-179, modules/gating.py:12-21).
+ * 1 <= M <= 128, K % 64 == 0.  The plan embeds the pointers. */
+typedef struct rstnet_skinny_plan rstnet_skinny_plan;
+int64_t rstnet_skinny_gemm_workspace(int32_t M, int32_t N, int32_t max_splits);
+int rstnet_skinny_gemm_create(const void* X, const void* W, const void* R, void* out, float* partial_ws,
+                              int32_t M, int32_t N, int32_t K, int32_t max_splits, rstnet_skinny_plan** plan);
+int rstnet_skinny_gemm_run(const rstnet_skinny_plan* plan, rstnet_stream_t stream);
+void rstnet_skinny_gemm_destroy(rstnet_skinny_plan* plan);
+
+/* ---- x[b] = sum_cb input_emb[cb][seq[b,cb+1]] + wte[seq[b,0]] with bf16 rounding after every add and
+ * an exact zero row for id -1 (GPT.forward_global, llama_streaming.py:680-687; ScaledEmbedding :493-517).
+ * seq: int64, row b at seq + b*seq_stride; tables_dev: device array of n_q table pointers. */
+int rstnet_lm_embed_sum_bf16(const int64_t* seq, int32_t seq_stride, const void* wte, const void* const* tables_dev,
+                             int32_t n_q, int32_t E, void* x, int32_t B, rstnet_stream_t stream);
+/* out[b] = table[ids[b*id_stride]] (zero row for id < 0): codecformer_text_emb / codecformer_emb (:738-742) */
+int rstnet_lm_embed_rows_bf16(const int64_t* ids, int32_t id_stride, const void* table, int32_t D, void* out, int32_t B,
+                              rstnet_stream_t stream);
+/* ---- RMSNorm, fp32 inside.  kyutai == 0: lit_model.RMSNorm (lit_model.py:707-714);
+ * kyutai != 0: modules/transformer.py:34-48 `_rms_norm` with dtype=float (eps added before the mean's rsqrt). */
+int rstnet_lm_rms_norm_bf16(const void* x, const void* w, void* y, int32_t rows, int32_t dim, float eps, int32_t kyutai,
+                            rstnet_stream_t stream);
+/* ---- rotate-half RoPE with the model's bf16 cos/sin tables at row *offset, + ring-KV append
+ * (lit_model.py:560-573, 620-634).  qkv [B][nh][3][hs] (litgpt interleave, llama_streaming.py:957-963);
+ * q_out [B][nh*hs]; kv [2][B][nh][cap][hs]. */
+int rstnet_lm_rope_kv_append_bf16(const void* qkv, const void* cos_tab, const void* sin_tab, const int64_t* offset,
+                                  void* q_out, void* kv, int32_t B, int32_t nh, int32_t hs, int32_t cap,
+                                  rstnet_stream_t stream);
+/* ---- single-query attention over the ring with RingKVCache.complete's position labels and the
+ * (pos_k>=0)&(delta>=0)&(delta<context) mask (llama_streaming.py:983-992), fp32 softmax. HBM-bound. */
+int rstnet_lm_ring_decode_attention_bf16(const void* q, const void* kv, const int64_t* offset, void* out, int32_t B,
+                                         int32_t nh, int32_t hs, int32_t cap, int32_t context, rstnet_stream_t stream);
+/* out[m][c] = silu(ab[m][c]) * ab[m][I + c]   (LLaMAMLP / ActivationGating) */
+int rstnet_lm_silu_mul_bf16(const void* ab, void* out, int32_t M, int32_t I, rstnet_stream_t stream);
+/* ---- depth transformer attention at codebook step `step` (keys 0..step, capacity dep_q <= 8, no RoPE):
+ * qkv [B][3][H][hd]; kvd [2][B][H][cap][hd] (modules/transformer.py:375-419 with weights_per_step). */
+int rstnet_lm_depth_attention_bf16(const void* qkv, void* kvd, void* out, int32_t B, int32_t H, int32_t hd, int32_t cap,
+                                   int32_t step, rstnet_stream_t stream);
+/* ---- sample_token / sample_token_audio[_2048] (utils/sampling.py:85-154): ids restricted to [0, n_valid);
+ * top_k <= 0 -> argmax (first maximum); else top-k + temperature + exponential-noise multinomial with a
+ * counter-based RNG keyed by (seed, *step_counter, row).  tokens[row*tok_stride] = id. */
+int rstnet_lm_sample_bf16(const void* logits, int32_t rows, int32_t V, int32_t n_valid, int32_t top_k, float temp,
+                          uint32_t seed, const int64_t* step_counter, int64_t* tokens, int32_t tok_stride,
+                          rstnet_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,9 @@ SYMBOLS = [
     "rstnet_counter_add", "rstnet_layer_norm_f32", "rstnet_rope_kv_append_f32",
     "rstnet_ring_attention_f32", "rstnet_rvq_encode_workspace", "rstnet_rvq_encode_f32",
     "rstnet_rvq_decode_gather_f32",
+    "rstnet_skinny_gemm_workspace", "rstnet_skinny_gemm_create", "rstnet_skinny_gemm_run", "rstnet_skinny_gemm_destroy",
+    "rstnet_lm_embed_sum_bf16", "rstnet_lm_embed_rows_bf16", "rstnet_lm_rms_norm_bf16", "rstnet_lm_rope_kv_append_bf16",
+    "rstnet_lm_ring_decode_attention_bf16", "rstnet_lm_silu_mul_bf16", "rstnet_lm_depth_attention_bf16", "rstnet_lm_sample_bf16",
 ]
 
 
@@ -97,6 +100,20 @@ def lib() -> C.CDLL:
     L.rstnet_rvq_encode_workspace.restype = i64
     L.rstnet_rvq_encode_f32.argtypes = [vp, i64, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, vp]
     L.rstnet_rvq_decode_gather_f32.argtypes = [vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, vp]
+    L.rstnet_skinny_gemm_workspace.argtypes = [i32, i32, i32]
+    L.rstnet_skinny_gemm_workspace.restype = i64
+    L.rstnet_skinny_gemm_create.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, C.POINTER(C.c_void_p)]
+    L.rstnet_skinny_gemm_run.argtypes = [vp, vp]
+    L.rstnet_skinny_gemm_destroy.argtypes = [vp]
+    L.rstnet_skinny_gemm_destroy.restype = None
+    L.rstnet_lm_embed_sum_bf16.argtypes = [vp, i32, vp, vp, i32, i32, vp, i32, vp]
+    L.rstnet_lm_embed_rows_bf16.argtypes = [vp, i32, vp, i32, vp, i32, vp]
+    L.rstnet_lm_rms_norm_bf16.argtypes = [vp, vp, vp, i32, i32, f32, i32, vp]
+    L.rstnet_lm_rope_kv_append_bf16.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    L.rstnet_lm_ring_decode_attention_bf16.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    L.rstnet_lm_silu_mul_bf16.argtypes = [vp, vp, i32, i32, vp]
+    L.rstnet_lm_depth_attention_bf16.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    L.rstnet_lm_sample_bf16.argtypes = [vp, i32, i32, i32, i32, f32, C.c_uint32, vp, vp, i32, vp]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("rstnet_version",):

@@ -1,0 +1,234 @@
+// Weight-streaming skinny GEMM for the LM decode step (tcgen05 kind::f16 / bf16, fp32 accumulate in
+// TMEM):   out[m, n] = sum_k X[m, k] * W[n, k]  (+ R[m, n]),   M = concurrent streams (<= 256).
+//
+// The step is HBM-bound (each bf16 weight is used for M MACs), so the design goal is to keep
+// 148 SMs pulling weight tiles at full rate: the weight matrix is the MMA "A" operand (128 rows of
+// W per CTA = UMMA M), the activations are the "B" operand (UMMA N = M rounded up to 16), both
+// K-major exactly as nn.Linear stores them, 6-stage TMA ring of 128x64 bf16 weight tiles, and
+// split-K across CTAs when N/128 alone cannot fill the machine (fp32 partials + finalize kernel).
+// Replaces F.linear in CausalSelfAttention / LLaMAMLP / lm_head (models/llama_streaming.py:935-998,
+// models/lit_model.py:399-403) and in the depth transformer (modules/transformer.py:155-179, gating.py:12-21).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "../../include/rstnet_b200.h"
+
+namespace rstnet {
+extern void count_launch();
+using namespace tc;
+
+constexpr int SK_BN = 128;      // weight rows per CTA (UMMA M)
+constexpr int SK_BK = 64;       // bf16 elements per 128-byte swizzle row
+constexpr int SK_W_BYTES = SK_BN * 128;
+constexpr int SK_THREADS = 192; // TMA, MMA, 4 epilogue warps
+
+struct SkParams {
+  __nv_bfloat16* out;        // [M][N] bf16 (splits == 1)
+  float* partial;            // [splits][M][N] fp32 (splits > 1)
+  const __nv_bfloat16* R;    // optional residual [M][N]
+  int M, N, K, MB;           // MB = M rounded up to 16 (UMMA N)
+  int splits, k_iters;       // k_iters = 64-element chunks per split
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(SK_THREADS, 1)
+gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const SkParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int x_bytes = p.MB * 128;
+  const int stage_bytes = SK_W_BYTES + ((x_bytes + 1023) & ~1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int n0 = blockIdx.x * SK_BN;
+  const int split = blockIdx.y;
+  const int k_begin = split * p.k_iters;
+  int k_count = p.K / SK_BK - k_begin;
+  if (k_count > p.k_iters) k_count = p.k_iters;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<256>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    for (int kit = 0; kit < k_count; ++kit) {
+      const int s = kit % STAGES;
+      const uint32_t ph = (kit / STAGES) & 1;
+      mbar_wait(&empty[s], ph ^ 1);
+      if (elect_one()) {
+        uint8_t* st = smem + s * stage_bytes;
+        mbar_arrive_expect_tx(&full[s], SK_W_BYTES + x_bytes);
+        tma_load_2d(st, &tmW, &full[s], (k_begin + kit) * SK_BK, n0);
+        tma_load_2d(st + SK_W_BYTES, &tmX, &full[s], (k_begin + kit) * SK_BK, 0);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = instr_desc(1u, SK_BN, (uint32_t)p.MB);
+    for (int kit = 0; kit < k_count; ++kit) {
+      const int s = kit % STAGES;
+      const uint32_t ph = (kit / STAGES) & 1;
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        uint8_t* st = smem + s * stage_bytes;
+        const uint64_t dw = smem_desc_sw128(smem_u32(st)), dx = smem_desc_sw128(smem_u32(st + SK_W_BYTES));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // 4 x (K = 16 bf16 = 32 bytes)
+          mma_f16(tmem_base, dw + (uint64_t)(2 * k), dx + (uint64_t)(2 * k), idesc, (kit > 0 || k > 0) ? 1u : 0u);
+        tc_commit(&empty[s]);
+        if (kit == k_count - 1) tc_commit(tmem_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // epilogue: thread = one weight row n; TMEM columns = streams m
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int q = warp % 4;
+    const int n = n0 + q * 32 + lane;
+    const bool nv = n < p.N;
+    for (int c0 = 0; c0 < p.MB; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld_wait();
+      if (nv) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int m = c0 + j;
+          if (m < p.M) {
+            float v = __uint_as_float(r[j]);
+            if (p.splits > 1) {
+              p.partial[((long long)split * p.M + m) * p.N + n] = v;
+            } else {
+              if (p.R) v += __bfloat162float(p.R[(long long)m * p.N + n]);
+              p.out[(long long)m * p.N + n] = __float2bfloat16(v);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<256>(tmem_base);
+}
+
+__global__ void skinny_finalize_kernel(const float* __restrict__ partial, const __nv_bfloat16* __restrict__ R,
+                                       __nv_bfloat16* __restrict__ out, long long MN, int splits) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < MN; i += (long long)gridDim.x * blockDim.x) {
+    float v = 0.f;
+    for (int s = 0; s < splits; ++s) v += partial[(long long)s * MN + i];
+    if (R) v += __bfloat162float(R[i]);
+    out[i] = __float2bfloat16(v);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn2 get_encode_fn2() {
+  static EncodeTiledFn2 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && p) fn = (EncodeTiledFn2)p;
+  }
+  return fn;
+}
+}  // namespace rstnet
+using namespace rstnet;
+
+struct rstnet_skinny_plan {
+  CUtensorMap tmW, tmX;
+  SkParams p;
+  dim3 grid;
+  size_t smem;
+};
+
+extern "C" int rstnet_skinny_gemm_create(const void* X, const void* W, const void* R, void* out, float* partial_ws,
+                                         int32_t M, int32_t N, int32_t K, int32_t max_splits, rstnet_skinny_plan** outp) {
+  RSTNET_REQUIRE(X && W && out && outp, "skinny_gemm_create: null pointer");
+  RSTNET_REQUIRE(M >= 1 && M <= 128 && N >= 1 && K >= SK_BK && K % SK_BK == 0, "skinny_gemm_create: need 1<=M<=128, K %% 64 == 0 (M=%d N=%d K=%d)", M, N, K);
+  RSTNET_REQUIRE((uintptr_t)X % 16 == 0 && (uintptr_t)W % 16 == 0, "skinny_gemm_create: X and W must be 16-byte aligned");
+  EncodeTiledFn2 enc = get_encode_fn2();
+  RSTNET_REQUIRE(enc != nullptr, "skinny_gemm_create: cuTensorMapEncodeTiled unavailable");
+  rstnet_skinny_plan* pl = new rstnet_skinny_plan();
+  const int MB = ((M + 15) / 16) * 16;
+  const int n_tiles = ceil_div(N, SK_BN);
+  const int kchunks = K / SK_BK;
+  int splits = 1;
+  if (partial_ws && max_splits > 1) {
+    while (splits < max_splits && n_tiles * splits < 148 && kchunks / (splits * 2) >= 8) splits *= 2;
+  }
+  {
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    cuuint64_t gstr[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {SK_BK, SK_BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&pl->tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)W, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    cuuint64_t gdx[2] = {(cuuint64_t)K, (cuuint64_t)M};
+    cuuint32_t bx[2] = {SK_BK, (cuuint32_t)MB};
+    if (r == CUDA_SUCCESS)
+      r = enc(&pl->tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)X, gdx, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      delete pl;
+      set_error("skinny_gemm_create: cuTensorMapEncodeTiled failed with %d", (int)r);
+      return 3;
+    }
+  }
+  SkParams& p = pl->p;
+  p.out = (__nv_bfloat16*)out; p.partial = partial_ws; p.R = (const __nv_bfloat16*)R;
+  p.M = M; p.N = N; p.K = K; p.MB = MB; p.splits = splits;
+  p.k_iters = ceil_div(kchunks, splits);
+  pl->grid = dim3((unsigned)n_tiles, (unsigned)splits);
+  const int stage_bytes = SK_W_BYTES + ((MB * 128 + 1023) & ~1023);
+  pl->smem = (size_t)6 * stage_bytes + 1024 + 256;
+  *outp = pl;
+  return 0;
+}
+
+extern "C" int rstnet_skinny_gemm_run(const rstnet_skinny_plan* pl, rstnet_stream_t stream) {
+  RSTNET_REQUIRE(pl != nullptr, "skinny_gemm_run: null plan");
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(gemm_skinny_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    attr = true;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  gemm_skinny_kernel<6><<<pl->grid, SK_THREADS, pl->smem, st>>>(pl->tmW, pl->tmX, pl->p);
+  count_launch();
+  if (int e = check_launch("gemm_skinny")) return e;
+  if (pl->p.splits > 1) {
+    const long long MN = (long long)pl->p.M * pl->p.N;
+    int g = ceil_div(MN, 256);
+    if (g > 148 * 4) g = 148 * 4;
+    skinny_finalize_kernel<<<g, 256, 0, st>>>(pl->p.partial, pl->p.R, pl->p.out, MN, pl->p.splits);
+    count_launch();
+    return check_launch("skinny_finalize");
+  }
+  return 0;
+}
+
+extern "C" void rstnet_skinny_gemm_destroy(rstnet_skinny_plan* pl) { delete pl; }
+extern "C" int64_t rstnet_skinny_gemm_workspace(int32_t M, int32_t N, int32_t max_splits) {
+  return (int64_t)max_splits * M * N * (int64_t)sizeof(float);
+}

@@ -1,0 +1,396 @@
+// HBM-bound bf16 kernels of the speech-text LM decode step: embedding sum, RMSNorm (two variants),
+// rotate-half RoPE + ring-KV append, ring decode attention, SiLU gating, depth-transformer attention,
+// embedding gather, greedy / top-k sampling.  One token per stream (T == 1): rows are streams.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "../../include/rstnet_b200.h"
+
+namespace rstnet {
+extern void count_launch();
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float b2f(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ bf16 f2b(float v) { return __float2bfloat16(v); }
+
+// ---------------------------------------------------------------- embedding sum (llama_streaming.py:680-687)
+// x[b] = ((e_0 + e_1) + ... + e_{nq-1}) + wte[text]; every add rounds to bf16 as the eager bf16 model does;
+// id -1 contributes an exact zero row (ScaledEmbedding, :505-517).
+__global__ void embed_sum_kernel(const long long* __restrict__ seq, int seq_stride, const bf16* __restrict__ wte,
+                                 const bf16* const* __restrict__ tables, int n_q, int E, bf16* __restrict__ x) {
+  const int b = blockIdx.x;
+  const long long* ids = seq + (long long)b * seq_stride;
+  for (int d = threadIdx.x; d < E; d += blockDim.x) {
+    float acc = 0.f;
+    for (int cb = 0; cb < n_q; ++cb) {
+      const long long id = ids[cb + 1];
+      const float e = id < 0 ? 0.f : b2f(tables[cb][id * E + d]);
+      acc = cb == 0 ? e : b2f(f2b(acc + e));
+    }
+    acc = b2f(f2b(acc + b2f(wte[ids[0] * E + d])));
+    x[(long long)b * E + d] = f2b(acc);
+  }
+}
+
+// out[b] = table[id[b]] (zero row for id < 0): depth-transformer token embeddings (llama_streaming.py:738-742)
+__global__ void embed_rows_kernel(const long long* __restrict__ ids, int id_stride, const bf16* __restrict__ table, int D,
+                                  bf16* __restrict__ out) {
+  const int b = blockIdx.x;
+  const long long id = ids[(long long)b * id_stride];
+  for (int d = threadIdx.x; d < D; d += blockDim.x) out[(long long)b * D + d] = id < 0 ? f2b(0.f) : table[id * D + d];
+}
+
+// ---------------------------------------------------------------- RMSNorm, fp32 inside (lit_model.py:707-714;
+// kyutai variant modules/transformer.py:34-48: var = eps + mean(x^2); y = x * (alpha * rsqrt(var)))
+__global__ void rms_norm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y, int dim, float eps,
+                                int kyutai) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const bf16* xr = x + (long long)b * dim;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) { const float v = b2f(xr[i]); s = fmaf(v, v, s); }
+  s = warp_sum(s);
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < blockDim.x / 32 ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) red[0] = t;
+  }
+  __syncthreads();
+  const float mean = red[0] / (float)dim;
+  const float r = kyutai ? rsqrtf(eps + mean) : rsqrtf(mean + eps);
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+    const float v = b2f(xr[i]);
+    const float o = kyutai ? v * (b2f(w[i]) * r) : (v * r) * b2f(w[i]);
+    y[(long long)b * dim + i] = f2b(o);
+  }
+}
+
+// ---------------------------------------------------------------- RoPE (rotate-half, bf16 cos/sin rows) + KV ring append
+// qkv [B][nh][3][hs] (litgpt per-group interleave, llama_streaming.py:957-963); writes rotated q to q_out [B][nh*hs],
+// rotated k and v into kv[2][B][nh][cap][hs] at slot (*offset % cap)  (lit_model.py:560-573, 620-634).
+__global__ void rope_kv_append_bf16_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ cosb, const bf16* __restrict__ sinb,
+                                           const long long* __restrict__ offset, bf16* __restrict__ q_out, bf16* __restrict__ kv,
+                                           int B, int nh, int hs, int cap) {
+  const int b = blockIdx.x / nh, h = blockIdx.x % nh;
+  const long long pos = *offset;
+  const int slot = (int)(pos % cap);
+  const bf16* base = qkv + ((long long)b * nh + h) * 3 * hs;
+  const bf16* c = cosb + pos * hs;
+  const bf16* s = sinb + pos * hs;
+  bf16* kdst = kv + (((long long)b * nh + h) * cap + slot) * hs;
+  bf16* vdst = kv + (long long)B * nh * cap * hs + (((long long)b * nh + h) * cap + slot) * hs;
+  const int half = hs / 2;
+  for (int d = threadIdx.x; d < hs; d += blockDim.x) {
+    const float cd = b2f(c[d]), sd = b2f(s[d]);
+    // roped = (x * cos) + (rotated * sin), each op rounded to bf16 as the eager bf16 model does
+    const float qx = b2f(base[d]), kx = b2f(base[hs + d]);
+    const float qr = d < half ? -b2f(base[d + half]) : b2f(base[d - half]);
+    const float kr = d < half ? -b2f(base[hs + d + half]) : b2f(base[hs + d - half]);
+    const float qv = b2f(f2b(b2f(f2b(qx * cd)) + b2f(f2b(qr * sd))));
+    const float kvv = b2f(f2b(b2f(f2b(kx * cd)) + b2f(f2b(kr * sd))));
+    q_out[((long long)b * nh + h) * hs + d] = f2b(qv);
+    kdst[d] = f2b(kvv);
+    vdst[d] = base[2 * hs + d];
+  }
+}
+
+// ---------------------------------------------------------------- ring decode attention (T == 1)
+// one CTA per (head, stream); 8 lanes share a key row (16 dims = 32 bytes each, so a warp load covers 4 whole
+// 256-byte rows = 1 KB contiguous); per-group online softmax, combined across groups / warps at the end.
+// Mask = RingKVCache.complete + (pos_k>=0)&(delta>=0)&(delta<context) (llama_streaming.py:983-992).
+template <int HS>
+__global__ void __launch_bounds__(256) ring_decode_attention_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kv,
+                                                                    const long long* __restrict__ offset, bf16* __restrict__ out,
+                                                                    int B, int nh, int cap, int context, float scale) {
+  constexpr int DPL = HS / 8;  // dims per lane
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int grp = lane / 8, sub = lane % 8;
+  const int nwarps = blockDim.x / 32;
+  const long long pos = *offset;  // position of the query; its key/value were appended just before
+  long long lo = pos - context + 1;
+  if (lo < 0) lo = 0;
+  if (lo < pos + 2 - cap) lo = pos + 2 - cap;  // ring quirk: the oldest slot is labelled end_offset and masked
+  const long long nkeys = pos - lo + 1;
+  const bf16* Kb = kv + ((long long)b * nh + h) * cap * HS;
+  const bf16* Vb = Kb + (long long)B * nh * cap * HS;
+  float qf[DPL];
+  {
+    const bf16* qp = q + ((long long)b * nh + h) * HS + sub * DPL;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) qf[i] = b2f(qp[i]);
+  }
+  float m = -INFINITY, l = 0.f, acc[DPL];
+#pragma unroll
+  for (int i = 0; i < DPL; ++i) acc[i] = 0.f;
+  for (long long j0 = (long long)warp * 4; j0 < nkeys; j0 += (long long)nwarps * 4) {
+    const long long j = j0 + grp;
+    const bool valid = j < nkeys;
+    const int slot = (int)((lo + (valid ? j : 0)) % cap);
+    const uint4* kp = reinterpret_cast<const uint4*>(Kb + (long long)slot * HS + sub * DPL);
+    const uint4* vp = reinterpret_cast<const uint4*>(Vb + (long long)slot * HS + sub * DPL);
+    uint4 kr[DPL / 8], vr[DPL / 8];
+#pragma unroll
+    for (int i = 0; i < DPL / 8; ++i) { kr[i] = kp[i]; vr[i] = vp[i]; }
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < DPL / 8; ++i) {
+      const bf16* kk = reinterpret_cast<const bf16*>(&kr[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dot = fmaf(qf[i * 8 + e], b2f(kk[e]), dot);
+    }
+    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+    if (valid) {
+      const float s = dot * scale;
+      const float m_new = fmaxf(m, s);
+      const float corr = __expf(m - m_new), pj = __expf(s - m_new);
+      l = l * corr + pj;
+#pragma unroll
+      for (int i = 0; i < DPL / 8; ++i) {
+        const bf16* vv = reinterpret_cast<const bf16*>(&vr[i]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[i * 8 + e] = fmaf(pj, b2f(vv[e]), acc[i * 8 + e] * corr);
+      }
+      m = m_new;
+    }
+  }
+  // combine the 4 key groups of the warp (lanes sub, sub+8, sub+16, sub+24 hold the same dims)
+#pragma unroll
+  for (int o = 8; o <= 16; o <<= 1) {
+    const float mo = __shfl_xor_sync(0xffffffffu, m, o), lo_ = __shfl_xor_sync(0xffffffffu, l, o);
+    const float mn = fmaxf(m, mo);
+    const float ca = mn == -INFINITY ? 0.f : __expf(m - mn), cb = mn == -INFINITY ? 0.f : __expf(mo - mn);
+    l = l * ca + lo_ * cb;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) acc[i] = acc[i] * ca + __shfl_xor_sync(0xffffffffu, acc[i], o) * cb;
+    m = mn;
+  }
+  __shared__ float sm_m[8], sm_l[8], sm_acc[8][HS];
+  if (grp == 0) {
+    if (sub == 0) { sm_m[warp] = m; sm_l[warp] = l; }
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) sm_acc[warp][sub * DPL + i] = acc[i];
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < HS; d += blockDim.x) {
+    float mm = -INFINITY;
+    for (int w = 0; w < nwarps; ++w) mm = fmaxf(mm, sm_m[w]);
+    float ll = 0.f, a = 0.f;
+    for (int w = 0; w < nwarps; ++w) {
+      const float c = sm_m[w] == -INFINITY ? 0.f : __expf(sm_m[w] - mm);
+      ll += sm_l[w] * c;
+      a += sm_acc[w][d] * c;
+    }
+    out[((long long)b * nh + h) * HS + d] = f2b(a / ll);
+  }
+}
+
+// ---------------------------------------------------------------- SiLU gating: out = silu(a) * b  (bf16 roundings as eager)
+// ab [M][2*I] with a = cols [0,I), b = cols [I,2I) (fused fc_1|fc_2, or gating's view(B,T,2,-1), gating.py:16-19)
+__global__ void silu_mul_kernel(const bf16* __restrict__ ab, bf16* __restrict__ out, int M, int I) {
+  const long long total = (long long)M * I;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / I, c = i % I;
+    const float a = b2f(ab[m * 2 * I + c]), b = b2f(ab[m * 2 * I + I + c]);
+    const float s = b2f(f2b(a / (1.0f + expf(-a))));
+    out[i] = f2b(s * b);
+  }
+}
+
+// ---------------------------------------------------------------- depth-transformer attention (<= 8 keys, no RoPE)
+// qkv [B][3][H][hd] ((p h d) layout, transformer.py:391-393); kvd [2][B][H][cap][hd]; step k: append at slot k,
+// attend keys 0..k (cap == dep_q so the ring never wraps inside a frame).
+__global__ void depth_attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kvd, bf16* __restrict__ out, int B, int H,
+                                       int hd, int cap, int step) {
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int lane = threadIdx.x;
+  const int HD = H * hd;
+  const bf16* qp = qkv + (long long)b * 3 * HD + h * hd;
+  bf16* Kb = kvd + (((long long)b * H + h) * cap) * hd;
+  bf16* Vb = Kb + (long long)B * H * cap * hd;
+  for (int d = lane; d < hd; d += 32) {
+    Kb[(long long)step * hd + d] = qp[HD + d];
+    Vb[(long long)step * hd + d] = qp[2 * HD + d];
+  }
+  __syncwarp();
+  const float scale = rsqrtf((float)hd);
+  float sc[8];
+  float mx = -INFINITY;
+  // RingKVCache.complete labels slot end_offset % capacity with position end_offset (modules/transformer.py:258-263),
+  // so on the last codebook step (end_offset == capacity) key 0 is masked by `delta >= 0`.
+  const int j_lo = step + 2 - cap > 0 ? step + 2 - cap : 0;
+  for (int j = j_lo; j <= step; ++j) {
+    float dot = 0.f;
+    for (int d = lane; d < hd; d += 32) dot = fmaf(b2f(qp[d]), b2f(Kb[(long long)j * hd + d]), dot);
+    dot = warp_sum(dot) * scale;
+    sc[j] = dot;
+    mx = fmaxf(mx, dot);
+  }
+  float l = 0.f;
+  for (int j = j_lo; j <= step; ++j) { sc[j] = __expf(sc[j] - mx); l += sc[j]; }
+  for (int d = lane; d < hd; d += 32) {
+    float a = 0.f;
+    for (int j = j_lo; j <= step; ++j) a = fmaf(sc[j], b2f(Vb[(long long)j * hd + d]), a);
+    out[(long long)b * HD + h * hd + d] = f2b(a / l);
+  }
+}
+
+// ---------------------------------------------------------------- sampling (utils/sampling.py:85-154)
+__device__ __forceinline__ uint32_t hash_u32(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  uint32_t h = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u ^ (c + 0x165667B1u) * 0xC2B2AE3Du ^ (d * 0x27D4EB2Fu);
+  h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+  return h;
+}
+
+// logits [rows][V] bf16, candidates restricted to ids < n_valid.  top_k <= 0: argmax (first maximum).
+// top_k > 0: the top_k largest logits, weights exp((l - max)/temp), token = argmax_i w_i / Exp(1)_i
+// (= torch's exponential-noise multinomial over the top-k probabilities, sampling.py:43-46, 57-59).
+__global__ void sample_kernel(const bf16* __restrict__ logits, int V, int n_valid, int top_k, float temp, uint32_t seed,
+                              const long long* __restrict__ step_counter, long long* __restrict__ tokens, int tok_stride) {
+  __shared__ float s_val[32];
+  __shared__ int s_idx[32];
+  __shared__ float top_v[64];
+  __shared__ int top_i[64];
+  const int row = blockIdx.x;
+  const bf16* lr = logits + (long long)row * V;
+  const int kk = top_k <= 0 ? 1 : (top_k > 64 ? 64 : top_k);
+  float last_v = INFINITY;
+  int last_i = -1;
+  for (int r = 0; r < kk; ++r) {
+    // largest (value, lowest index) strictly after (last_v, last_i) in the order (value desc, index asc)
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < n_valid; i += blockDim.x) {
+      const float v = b2f(lr[i]);
+      const bool after = v < last_v || (v == last_v && i > last_i);
+      if (after && (v > bv || (v == bv && i < bi))) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (threadIdx.x % 32 == 0) { s_val[threadIdx.x / 32] = bv; s_idx[threadIdx.x / 32] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      bv = threadIdx.x < blockDim.x / 32 ? s_val[threadIdx.x] : -INFINITY;
+      bi = threadIdx.x < blockDim.x / 32 ? s_idx[threadIdx.x] : 0x7fffffff;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (threadIdx.x == 0) { top_v[r] = bv; top_i[r] = bi; }
+    }
+    __syncthreads();
+    last_v = top_v[r];
+    last_i = top_i[r];
+  }
+  if (threadIdx.x == 0) {
+    int pick = top_i[0];
+    if (top_k > 0) {
+      const uint32_t stepc = step_counter ? (uint32_t)(*step_counter) : 0u;
+      float best = -INFINITY;
+      for (int r = 0; r < kk; ++r) {
+        const float w = expf((top_v[r] - top_v[0]) / temp);
+        const uint32_t u = hash_u32(seed, stepc, (uint32_t)row, (uint32_t)r);
+        const float uni = ((float)(u >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
+        const float e = -logf(uni);                                        // Exp(1)
+        const float score = w / e;
+        if (score > best) { best = score; pick = top_i[r]; }
+      }
+    }
+    tokens[(long long)row * tok_stride] = pick;
+  }
+}
+
+}  // namespace rstnet
+using namespace rstnet;
+
+extern "C" int rstnet_lm_embed_sum_bf16(const int64_t* seq, int32_t seq_stride, const void* wte, const void* const* tables_dev,
+                                        int32_t n_q, int32_t E, void* x, int32_t B, rstnet_stream_t stream) {
+  RSTNET_REQUIRE(seq && wte && tables_dev && x && B > 0, "lm_embed_sum: bad argument");
+  embed_sum_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const long long*)seq, seq_stride, (const bf16*)wte,
+                                                        (const bf16* const*)tables_dev, n_q, E, (bf16*)x);
+  count_launch();
+  return check_launch("lm_embed_sum");
+}
+
+extern "C" int rstnet_lm_embed_rows_bf16(const int64_t* ids, int32_t id_stride, const void* table, int32_t D, void* out, int32_t B,
+                                         rstnet_stream_t stream) {
+  RSTNET_REQUIRE(ids && table && out && B > 0, "lm_embed_rows: bad argument");
+  embed_rows_kernel<<<B, 128, 0, (cudaStream_t)stream>>>((const long long*)ids, id_stride, (const bf16*)table, D, (bf16*)out);
+  count_launch();
+  return check_launch("lm_embed_rows");
+}
+
+extern "C" int rstnet_lm_rms_norm_bf16(const void* x, const void* w, void* y, int32_t rows, int32_t dim, float eps, int32_t kyutai,
+                                       rstnet_stream_t stream) {
+  RSTNET_REQUIRE(x && w && y && rows > 0 && dim > 0, "lm_rms_norm: bad argument");
+  rms_norm_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)w, (bf16*)y, dim, eps, kyutai);
+  count_launch();
+  return check_launch("lm_rms_norm");
+}
+
+extern "C" int rstnet_lm_rope_kv_append_bf16(const void* qkv, const void* cos_tab, const void* sin_tab, const int64_t* offset,
+                                             void* q_out, void* kv, int32_t B, int32_t nh, int32_t hs, int32_t cap,
+                                             rstnet_stream_t stream) {
+  RSTNET_REQUIRE(qkv && cos_tab && sin_tab && offset && q_out && kv, "lm_rope_kv_append: null pointer");
+  rope_kv_append_bf16_kernel<<<B * nh, 64, 0, (cudaStream_t)stream>>>((const bf16*)qkv, (const bf16*)cos_tab, (const bf16*)sin_tab,
+                                                                      (const long long*)offset, (bf16*)q_out, (bf16*)kv, B, nh, hs, cap);
+  count_launch();
+  return check_launch("lm_rope_kv_append");
+}
+
+extern "C" int rstnet_lm_ring_decode_attention_bf16(const void* q, const void* kv, const int64_t* offset, void* out, int32_t B,
+                                                    int32_t nh, int32_t hs, int32_t cap, int32_t context, rstnet_stream_t stream) {
+  RSTNET_REQUIRE(q && kv && offset && out, "lm_ring_decode_attention: null pointer");
+  RSTNET_REQUIRE(hs == 128 || hs == 64, "lm_ring_decode_attention: head_size must be 64 or 128 (got %d)", hs);
+  const float scale = 1.0f / sqrtf((float)hs);
+  dim3 grid(nh, B);
+  if (hs == 128)
+    ring_decode_attention_kernel<128><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)q, (const bf16*)kv, (const long long*)offset,
+                                                                               (bf16*)out, B, nh, cap, context, scale);
+  else
+    ring_decode_attention_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)q, (const bf16*)kv, (const long long*)offset,
+                                                                              (bf16*)out, B, nh, cap, context, scale);
+  count_launch();
+  return check_launch("lm_ring_decode_attention");
+}
+
+extern "C" int rstnet_lm_silu_mul_bf16(const void* ab, void* out, int32_t M, int32_t I, rstnet_stream_t stream) {
+  RSTNET_REQUIRE(ab && out && M > 0 && I > 0, "lm_silu_mul: bad argument");
+  const long long total = (long long)M * I;
+  int g = ceil_div(total, 256);
+  if (g > 148 * 8) g = 148 * 8;
+  silu_mul_kernel<<<g, 256, 0, (cudaStream_t)stream>>>((const bf16*)ab, (bf16*)out, M, I);
+  count_launch();
+  return check_launch("lm_silu_mul");
+}
+
+extern "C" int rstnet_lm_depth_attention_bf16(const void* qkv, void* kvd, void* out, int32_t B, int32_t H, int32_t hd, int32_t cap,
+                                              int32_t step, rstnet_stream_t stream) {
+  RSTNET_REQUIRE(qkv && kvd && out, "lm_depth_attention: null pointer");
+  RSTNET_REQUIRE(step >= 0 && step < cap && cap <= 8, "lm_depth_attention: step %d / capacity %d (<= 8) out of range", step, cap);
+  depth_attention_kernel<<<B * H, 32, 0, (cudaStream_t)stream>>>((const bf16*)qkv, (bf16*)kvd, (bf16*)out, B, H, hd, cap, step);
+  count_launch();
+  return check_launch("lm_depth_attention");
+}
+
+extern "C" int rstnet_lm_sample_bf16(const void* logits, int32_t rows, int32_t V, int32_t n_valid, int32_t top_k, float temp,
+                                     uint32_t seed, const int64_t* step_counter, int64_t* tokens, int32_t tok_stride,
+                                     rstnet_stream_t stream) {
+  RSTNET_REQUIRE(logits && tokens && rows > 0 && V > 0, "lm_sample: bad argument");
+  RSTNET_REQUIRE(top_k <= 64 && (top_k <= 0 || temp > 0.f), "lm_sample: top_k <= 64 and temp > 0 required");
+  if (n_valid <= 0 || n_valid > V) n_valid = V;
+  sample_kernel<<<rows, 1024, 0, (cudaStream_t)stream>>>((const bf16*)logits, V, n_valid, top_k, temp, seed,
+                                                         (const long long*)step_counter, (long long*)tokens, tok_stride);
+  count_launch();
+  return check_launch("lm_sample");
+}
