@@ -248,6 +248,15 @@ def run_ours(args):
         roof = roofline_pass(m, x_dev, B, dev)
         cpu_threads = best_cpu_threads()
         cv, cdt = cpu_sample(8, 4, cpu_threads)
+        lm = None
+        if world == 1 and not args.no_lm:
+            m._stream_state = None
+            m._engine = None
+            torch.cuda.empty_cache()
+            try:
+                lm = lm_decode_bench(dev, steps=10, warmup=3)
+            except Exception as e:  # the codec headline must not be lost to an LM-side failure
+                lm = {"error": f"{type(e).__name__}: {e}"[:300]}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -261,6 +270,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": B * FRAMES * (FRAME * 4 + 8 * 8), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches_per_frame * FRAMES * args.steps),
             "roofline": roof,
+            "lm_decode": lm,
             "cpu_baseline": {"value": cv, "unit": UNIT, "cores": cpu_threads, "host_cores": os.cpu_count(), "kind": "port",
                              "sample": f"8 streams x 4 frames streaming encode+decode, torch CPU fp32 oracle port ({cdt:.1f} s)"},
         }
@@ -320,6 +330,113 @@ def roofline_pass(m, x_dev, B, dev):
             "gflop_per_frame_batch": flops / nframes / 1e9}
 
 
+def lm_decode_bench(dev, steps: int, warmup: int):
+    """BASELINE.json configs[2]: one decode step (temporal 32-layer 7B + 8 depth steps + sampling) of the
+    speech-text LM, random-init bf16 weights, batch 64 streams, KV ring pre-filled to 2048 positions.
+    Reported next to the codec headline (it is a different unit of work, not part of `value`)."""
+    import torch
+    from rstnet_b200 import _lib, ops
+    from rstnet_b200 import lm as LMmod
+    from rstnet_b200.lm import GPT, Config
+    peaks = _peaks()
+    B, KV = 64, 2048
+    cfg = Config(block_size=4096, n_layer=32, n_embd=4096, n_head=32, head_size=128, intermediate_size=11008,
+                 padded_vocab_size=152064, audio_card=2050, n_q=8, dep_q=8, codecformer_dim=1024, codecformer_heads=16,
+                 codecformer_layers=6, codecformer_dim_feedforward=4224, context=KV)
+    m = GPT(cfg, device=dev, dtype=torch.bfloat16).eval()
+    n_params = sum(p.numel() for p in m.parameters())
+    # per-launch accounting hooks (bound when the scope's plans are built)
+    rec = {"gemm": [], "attn": []}
+    timing = {"on": False}
+    orig_run = LMmod.SkinnyGemm.run
+    L = _lib.lib()
+    orig_attn = L.rstnet_lm_ring_decode_attention_bf16
+
+    def timed_run(self):
+        if not timing["on"]:
+            return orig_run(self)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); orig_run(self); e1.record()
+        rec["gemm"].append((e0, e1, self.bytes, tuple(self._keep[1].shape)))
+
+    def timed_attn(*a):
+        if not timing["on"]:
+            return orig_attn(*a)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); r = orig_attn(*a); e1.record()
+        rec["attn"].append((e0, e1, 2.0 * B * cfg.n_head * (KV - 1) * cfg.head_size * 2))
+        return r
+
+    LMmod.SkinnyGemm.run = timed_run
+    L.rstnet_lm_ring_decode_attention_bf16 = timed_attn
+    try:
+        m.streaming_forever(B)
+        st = m._state
+        for kv in st.kv:
+            kv.normal_()
+        st.offset.fill_(KV + 8)  # ring already wrapped: every step attends the full window
+        g = torch.Generator(device=dev).manual_seed(0)
+        seq = torch.randint(0, 2048, (B, 9, 1), device=dev, generator=g)
+        seq[:, 0] = torch.randint(0, 128256, (B, 1), device=dev, generator=g)
+        host_seq = seq.cpu().pin_memory()
+        host_tok = torch.empty(B, 9, dtype=torch.int64).pin_memory()
+        m.use_cuda_graphs = True
+        for _ in range(max(3, warmup)):
+            m.forward_step(seq)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            m.forward_step(seq)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        e0.record()
+        for _ in range(steps):
+            t = m.forward_step(host_seq.to(dev, non_blocking=True))
+            host_tok.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_e2e = e0.elapsed_time(e1) / steps
+        # per-kernel roofline pass: one eager frame with events around every GEMM / attention launch
+        m.use_cuda_graphs = False
+        m.forward_step(seq)
+        timing["on"] = True
+        m.forward_step(seq)
+        torch.cuda.synchronize()
+        timing["on"] = False
+    finally:
+        LMmod.SkinnyGemm.run = orig_run
+        L.rstnet_lm_ring_decode_attention_bf16 = orig_attn
+
+    def agg(items):
+        t = sum(it[0].elapsed_time(it[1]) for it in items)
+        by = sum(it[2] for it in items)
+        return {"launches": len(items), "ms": t, "gbytes": by / 1e9, "achieved_gbs": by / 1e9 / (t * 1e-3) if t else None,
+                "frac": (by / 1e9 / (t * 1e-3)) / peaks["hbm_gbs"] if t else None}
+
+    w_bytes = 2.0 * n_params - 2.0 * (152064 * 4096 + 8 * 2051 * 4096 + 152064 * 1024 + 7 * 2051 * 1024)  # embeddings are gathered, not streamed
+    kv_bytes = 32 * 2.0 * B * 32 * (KV - 1) * 128 * 2
+    step_bytes = w_bytes + kv_bytes
+    out = {"workload": "gpt7b_decode_step_B64_kv2048 (32-layer temporal + 8x6-layer depth + sampling)", "dtype": "bf16",
+           "params": n_params, "ms_per_step": ms, "frames_per_s": B / (ms * 1e-3), "tokens_per_s": B * 9 / (ms * 1e-3),
+           "e2e_ms_per_step": ms_e2e, "e2e_tokens_per_s": B * 9 / (ms_e2e * 1e-3),
+           "algorithmic_gbytes_per_step": step_bytes / 1e9,
+           "roofline": {"bound": "hbm", "achieved": step_bytes / 1e9 / (ms * 1e-3), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": step_bytes / 1e9 / (ms * 1e-3) / peaks["hbm_gbs"], "peak_source": peaks["source"]},
+           "attention_kernel": agg(rec["attn"]), "gemm_kernels": agg(rec["gemm"])}
+    shapes = {}
+    for it in rec["gemm"]:
+        d = shapes.setdefault(str(it[3]), [0, 0.0, 0.0])
+        d[0] += 1; d[1] += it[0].elapsed_time(it[1]); d[2] += it[2]
+    out["gemm_by_shape_NK"] = {k: {"launches": v[0], "avg_us": 1e3 * v[1] / v[0], "gbs": v[2] / 1e9 / (v[1] * 1e-3)} for k, v in shapes.items()}
+    m._state = None
+    del m
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     global FRAMES, WORKLOAD
     ap = argparse.ArgumentParser()
@@ -327,6 +444,7 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-lm", dest="no_lm", action="store_true", help="skip the secondary LM decode-step measurement")
     ap.add_argument("--frames", type=int, default=FRAMES,
                     help="frames per stream per step (profiling aid: ncu runs use a short pass; the default 125 is the bench)")
     args = ap.parse_args()

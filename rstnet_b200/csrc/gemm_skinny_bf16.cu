@@ -4,7 +4,7 @@
 // The step is HBM-bound (each bf16 weight is used for M MACs), so the design goal is to keep
 // 148 SMs pulling weight tiles at full rate: the weight matrix is the MMA "A" operand (128 rows of
 // W per CTA = UMMA M), the activations are the "B" operand (UMMA N = M rounded up to 16), both
-// K-major exactly as nn.Linear stores them, 6-stage TMA ring of 128x64 bf16 weight tiles, and
+// K-major exactly as nn.Linear stores them, 4-stage TMA ring of 128x64 bf16 weight tiles, two CTAs per SM, and
 // split-K across CTAs when N/128 alone cannot fill the machine (fp32 partials + finalize kernel).
 // Replaces F.linear in CausalSelfAttention / LLaMAMLP / lm_head (models/llama_streaming.py:935-998,
 // models/lit_model.py:399-403) and in the depth transformer (modules/transformer.py:155-179, gating.py:12-21).
@@ -32,7 +32,7 @@ struct SkParams {
 };
 
 template <int STAGES>
-__global__ void __launch_bounds__(SK_THREADS, 1)
+__global__ void __launch_bounds__(SK_THREADS, 2)
 gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const SkParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -175,7 +175,7 @@ extern "C" int rstnet_skinny_gemm_create(const void* X, const void* W, const voi
   const int kchunks = K / SK_BK;
   int splits = 1;
   if (partial_ws && max_splits > 1) {
-    while (splits < max_splits && n_tiles * splits < 148 && kchunks / (splits * 2) >= 8) splits *= 2;
+    while (splits < max_splits && n_tiles * splits < 2 * 148 - 40 && kchunks / (splits * 2) >= 8) splits *= 2;
   }
   {
     cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)N};
@@ -201,7 +201,9 @@ extern "C" int rstnet_skinny_gemm_create(const void* X, const void* W, const voi
   p.k_iters = ceil_div(kchunks, splits);
   pl->grid = dim3((unsigned)n_tiles, (unsigned)splits);
   const int stage_bytes = SK_W_BYTES + ((MB * 128 + 1023) & ~1023);
-  pl->smem = (size_t)6 * stage_bytes + 1024 + 256;
+  // 4 stages (<= 98 KB with M <= 64): two CTAs fit per SM, so a GEMM whose tile count is not a multiple of 148
+  // still keeps every SM streaming (bandwidth-bound CTAs progress at equal rates) and prologues overlap main loops
+  pl->smem = (size_t)4 * stage_bytes + 1024 + 256;
   *outp = pl;
   return 0;
 }
@@ -210,11 +212,11 @@ extern "C" int rstnet_skinny_gemm_run(const rstnet_skinny_plan* pl, rstnet_strea
   RSTNET_REQUIRE(pl != nullptr, "skinny_gemm_run: null plan");
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(gemm_skinny_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(gemm_skinny_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  gemm_skinny_kernel<6><<<pl->grid, SK_THREADS, pl->smem, st>>>(pl->tmW, pl->tmX, pl->p);
+  gemm_skinny_kernel<4><<<pl->grid, SK_THREADS, pl->smem, st>>>(pl->tmW, pl->tmX, pl->p);
   count_launch();
   if (int e = check_launch("gemm_skinny")) return e;
   if (pl->p.splits > 1) {

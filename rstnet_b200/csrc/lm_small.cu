@@ -125,15 +125,23 @@ __global__ void __launch_bounds__(256) ring_decode_attention_kernel(const bf16* 
   float m = -INFINITY, l = 0.f, acc[DPL];
 #pragma unroll
   for (int i = 0; i < DPL; ++i) acc[i] = 0.f;
-  for (long long j0 = (long long)warp * 4; j0 < nkeys; j0 += (long long)nwarps * 4) {
+  // software pipeline: the K/V rows of the next iteration are in flight while this one is reduced
+  uint4 kr[DPL / 8], vr[DPL / 8], kn[DPL / 8], vn[DPL / 8];
+  auto load_rows = [&](long long j0, uint4* kd, uint4* vd) {
     const long long j = j0 + grp;
-    const bool valid = j < nkeys;
-    const int slot = (int)((lo + (valid ? j : 0)) % cap);
+    const int slot = (int)((lo + (j < nkeys ? j : 0)) % cap);
     const uint4* kp = reinterpret_cast<const uint4*>(Kb + (long long)slot * HS + sub * DPL);
     const uint4* vp = reinterpret_cast<const uint4*>(Vb + (long long)slot * HS + sub * DPL);
-    uint4 kr[DPL / 8], vr[DPL / 8];
 #pragma unroll
-    for (int i = 0; i < DPL / 8; ++i) { kr[i] = kp[i]; vr[i] = vp[i]; }
+    for (int i = 0; i < DPL / 8; ++i) { kd[i] = __ldg(kp + i); vd[i] = __ldg(vp + i); }
+  };
+  const long long jstep = (long long)nwarps * 4;
+  long long j0 = (long long)warp * 4;
+  if (j0 < nkeys) load_rows(j0, kr, vr);
+  for (; j0 < nkeys; j0 += jstep) {
+    const bool more = j0 + jstep < nkeys;
+    if (more) load_rows(j0 + jstep, kn, vn);
+    const bool valid = j0 + grp < nkeys;
     float dot = 0.f;
 #pragma unroll
     for (int i = 0; i < DPL / 8; ++i) {
@@ -156,6 +164,10 @@ __global__ void __launch_bounds__(256) ring_decode_attention_kernel(const bf16* 
         for (int e = 0; e < 8; ++e) acc[i * 8 + e] = fmaf(pj, b2f(vv[e]), acc[i * 8 + e] * corr);
       }
       m = m_new;
+    }
+    if (more) {
+#pragma unroll
+      for (int i = 0; i < DPL / 8; ++i) { kr[i] = kn[i]; vr[i] = vn[i]; }
     }
   }
   // combine the 4 key groups of the warp (lanes sub, sub+8, sub+16, sub+24 hold the same dims)

@@ -114,7 +114,9 @@ class _DepthScope:
 
 
 class GPT(nn.Module):
-    def __init__(self, config: Config):
+    def __init__(self, config: Config, device=None, dtype=None):
+        """device/dtype: create the (random-init) parameters directly there (a 7B model in bf16 on the GPU
+        without a 28 GB fp32 host copy); default = CPU fp32 like the reference constructor."""
         super().__init__()
         c = self.config = config
         if c.n_query_groups != c.n_head:
@@ -122,23 +124,27 @@ class GPT(nn.Module):
         if c.rotary_percentage != 1.0:
             raise NotImplementedError("partial rotary embeddings are not implemented")
         E, V, I, D, H = c.n_embd, c.padded_vocab_size, c.intermediate_size, c.codecformer_dim, c.ff_hidden
-        g = torch.Generator().manual_seed(0)
+        g = torch.Generator(device=device if device is not None else "cpu").manual_seed(0)
+        fk = dict(device=device, dtype=dtype)
 
         def w_(*shape):
-            return torch.empty(*shape).normal_(0.0, 0.02, generator=g)
+            return torch.empty(*shape, **fk).normal_(0.0, 0.02, generator=g)
+
+        def ones(*shape):
+            return torch.ones(*shape, **fk)
 
         _register(self, "lm_head.linear.weight", w_(V, E))
         _register(self, "transformer.wte.weight", w_(V, E))
         for l in range(c.n_layer):
             p = f"transformer.h.{l}"
-            _register(self, f"{p}.norm_1.weight", torch.ones(E))
+            _register(self, f"{p}.norm_1.weight", ones(E))
             _register(self, f"{p}.attn.attn.linear.weight", w_(3 * c.n_head * c.head_size, E))
             _register(self, f"{p}.attn.proj.linear.weight", w_(E, c.n_head * c.head_size))
-            _register(self, f"{p}.norm_2.weight", torch.ones(E))
+            _register(self, f"{p}.norm_2.weight", ones(E))
             _register(self, f"{p}.mlp.fc_1.linear.weight", w_(I, E))
             _register(self, f"{p}.mlp.fc_2.linear.weight", w_(I, E))
             _register(self, f"{p}.mlp.proj.linear.weight", w_(E, I))
-        _register(self, "transformer.ln_f.weight", torch.ones(E))
+        _register(self, "transformer.ln_f.weight", ones(E))
         for i in range(c.n_q):
             _register(self, f"input_emb.{i}.weight", w_(c.audio_card + 1, E))
         for i in range(c.dep_q):
@@ -150,8 +156,8 @@ class GPT(nn.Module):
             p = f"codecformer_.layers.{l}"
             _register(self, f"{p}.self_attn.in_proj_weight", w_(c.dep_q * 3 * D, D))
             _register(self, f"{p}.self_attn.out_proj.weight", w_(c.dep_q * D, D))
-            _register(self, f"{p}.norm1.alpha", torch.ones(1, 1, D))
-            _register(self, f"{p}.norm2.alpha", torch.ones(1, 1, D))
+            _register(self, f"{p}.norm1.alpha", ones(1, 1, D))
+            _register(self, f"{p}.norm2.alpha", ones(1, 1, D))
             for k in range(c.dep_q):
                 _register(self, f"{p}.gating.{k}.linear_in.weight", w_(2 * H, D))
                 _register(self, f"{p}.gating.{k}.linear_out.weight", w_(D, H))
@@ -338,12 +344,12 @@ class _LMState:
         self.table_ptrs = torch.tensor([t.data_ptr() for t in self.tables], dtype=torch.int64, device=dev)
         self.wte = P["transformer.wte.weight"]
         # split-K workspace shared by all GEMM plans (launches are stream-ordered)
-        self.ws = torch.empty(8 * B * max(E, 4096), dtype=torch.float32, device=dev)
+        self.ws = torch.empty(8 * B * max(3 * E, 2 * I, 4096), dtype=torch.float32, device=dev)
         if m._packed is None:
             m._packed = {f"fc12.{l}": torch.cat([P[f"transformer.h.{l}.mlp.fc_1.linear.weight"],
                                                  P[f"transformer.h.{l}.mlp.fc_2.linear.weight"]], 0).contiguous()
                          for l in range(c.n_layer)}
-        G = lambda X, W, out, R=None: SkinnyGemm(X, W, out, R, self.ws if W.shape[0] <= max(E, 4096) else None)
+        G = lambda X, W, out, R=None: SkinnyGemm(X, W, out, R, self.ws if W.shape[0] <= max(3 * E, 2 * I, 4096) else None)
         self.layers = []
         for l in range(c.n_layer):
             p = f"transformer.h.{l}"

@@ -8,6 +8,6 @@ echo "== bench" ; timeout 900 python bench.py --steps 3 --warmup 3 2>&1 | tail -
 if [ "$1" == "ncu" ]; then
   echo "== ncu launch list"
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1400 -c 400 --csv --log-file gpurun_out/launches.csv \
-      python bench.py --steps 1 --warmup 3 --frames 3 > gpurun_out/ncu_bench.log 2>&1
+      python bench.py --steps 1 --warmup 3 --frames 3 --no-lm > gpurun_out/ncu_bench.log 2>&1
   tail -3 gpurun_out/ncu_bench.log
 fi
