@@ -156,6 +156,7 @@ def run_ours(args):
     from oracle import mimi_spec as S  # seeded synthetic weights / audio only (no compute from oracle/)
     from rstnet_b200 import _lib, ops
     from rstnet_b200.codec import MimiCodec
+    from rstnet_b200.dist import reduce_timing
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -213,11 +214,7 @@ def run_ours(args):
             step(resident)
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms, _ = reduce_timing(e0.elapsed_time(e1), B * FRAMES * steps, device=dev)  # max over ranks
         return ms, _lib.launch_count() - l0
 
     # launches per frame (eager count; graph replays re-issue exactly these nodes)
