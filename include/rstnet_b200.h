@@ -205,6 +205,14 @@ typedef struct rstnet_skinny_plan rstnet_skinny_plan;
 int64_t rstnet_skinny_gemm_workspace(int32_t M, int32_t N, int32_t max_splits);
 int rstnet_skinny_gemm_create(const void* X, const void* W, const void* R, void* out, float* partial_ws,
                               int32_t M, int32_t N, int32_t K, int32_t max_splits, rstnet_skinny_plan** plan);
+/* Same GEMM with a fused finalize: fin_mode 1: out = bf16(acc + R) AND aux_out = RMSNorm(out) * norm_w (the pre-norm of
+ * the following GEMM: Block.forward's `x = attn + x; norm_2(x)`, llama_streaming.py:834-853; kyutai != 0 selects
+ * modules/transformer.py:34-48); fin_mode 2: aux_out[m][c] = silu(acc[m][c]) * acc[m][N/2 + c] (LLaMAMLP / ActivationGating),
+ * `out` unused.  Both need partial_ws. */
+int rstnet_skinny_gemm_create_fused(const void* X, const void* W, const void* R, void* out, float* partial_ws,
+                                    int32_t M, int32_t N, int32_t K, int32_t max_splits, int32_t fin_mode,
+                                    const void* norm_w, void* aux_out, float eps, int32_t kyutai,
+                                    rstnet_skinny_plan** plan);
 int rstnet_skinny_gemm_run(const rstnet_skinny_plan* plan, rstnet_stream_t stream);
 void rstnet_skinny_gemm_destroy(rstnet_skinny_plan* plan);
 

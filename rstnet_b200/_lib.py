@@ -21,7 +21,7 @@ SYMBOLS = [
     "rstnet_counter_add", "rstnet_layer_norm_f32", "rstnet_rope_kv_append_f32",
     "rstnet_ring_attention_f32", "rstnet_rvq_encode_workspace", "rstnet_rvq_encode_f32",
     "rstnet_rvq_decode_gather_f32",
-    "rstnet_skinny_gemm_workspace", "rstnet_skinny_gemm_create", "rstnet_skinny_gemm_run", "rstnet_skinny_gemm_destroy",
+    "rstnet_skinny_gemm_workspace", "rstnet_skinny_gemm_create", "rstnet_skinny_gemm_create_fused", "rstnet_skinny_gemm_run", "rstnet_skinny_gemm_destroy",
     "rstnet_lm_embed_sum_bf16", "rstnet_lm_embed_rows_bf16", "rstnet_lm_rms_norm_bf16", "rstnet_lm_rope_kv_append_bf16",
     "rstnet_lm_ring_decode_attention_bf16", "rstnet_lm_silu_mul_bf16", "rstnet_lm_depth_attention_bf16", "rstnet_lm_sample_bf16",
 ]
@@ -103,6 +103,7 @@ def lib() -> C.CDLL:
     L.rstnet_skinny_gemm_workspace.argtypes = [i32, i32, i32]
     L.rstnet_skinny_gemm_workspace.restype = i64
     L.rstnet_skinny_gemm_create.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, C.POINTER(C.c_void_p)]
+    L.rstnet_skinny_gemm_create_fused.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, f32, i32, C.POINTER(C.c_void_p)]
     L.rstnet_skinny_gemm_run.argtypes = [vp, vp]
     L.rstnet_skinny_gemm_destroy.argtypes = [vp]
     L.rstnet_skinny_gemm_destroy.restype = None

@@ -29,6 +29,7 @@ struct SkParams {
   const __nv_bfloat16* R;    // optional residual [M][N]
   int M, N, K, MB;           // MB = M rounded up to 16 (UMMA N)
   int splits, k_iters;       // k_iters = 64-element chunks per split
+  int force_partial;         // write fp32 partials even with one split (a fused finalize kernel consumes them)
 };
 
 template <int STAGES>
@@ -114,7 +115,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           const int m = c0 + j;
           if (m < p.M) {
             float v = __uint_as_float(r[j]);
-            if (p.splits > 1) {
+            if (p.splits > 1 || p.force_partial) {
               p.partial[((long long)split * p.M + m) * p.N + n] = v;
             } else {
               if (p.R) v += __bfloat162float(p.R[(long long)m * p.N + n]);
@@ -130,13 +131,97 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   if (warp == 1) tmem_dealloc<256>(tmem_base);
 }
 
+// plain finalize: out = bf16(sum_s partial[s] + R), 4 elements per thread (N % 4 == 0)
 __global__ void skinny_finalize_kernel(const float* __restrict__ partial, const __nv_bfloat16* __restrict__ R,
                                        __nv_bfloat16* __restrict__ out, long long MN, int splits) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < MN; i += (long long)gridDim.x * blockDim.x) {
-    float v = 0.f;
-    for (int s = 0; s < splits; ++s) v += partial[(long long)s * MN + i];
-    if (R) v += __bfloat162float(R[i]);
-    out[i] = __float2bfloat16(v);
+  const long long n4 = MN / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = *reinterpret_cast<const float4*>(partial + 4 * i);
+    for (int s = 1; s < splits; ++s) {
+      const float4 t = *reinterpret_cast<const float4*>(partial + (long long)s * MN + 4 * i);
+      v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+    }
+    if (R) {
+      const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(R + 4 * i);
+      const float2 a = __bfloat1622float2(r2[0]), b = __bfloat1622float2(r2[1]);
+      v.x += a.x; v.y += a.y; v.z += b.x; v.w += b.y;
+    }
+    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(out + 4 * i);
+    o2[0] = __floats2bfloat162_rn(v.x, v.y);
+    o2[1] = __floats2bfloat162_rn(v.z, v.w);
+  }
+}
+
+// finalize + residual + RMSNorm of the result in one pass over the row (one CTA per stream):
+//   out[m] = bf16(sum_s partial[s][m] + R[m]);  aux[m] = rmsnorm(out[m]) * w   (the NEXT op's pre-norm)
+// Replaces three kernels (finalize, residual add, RMSNorm) between a projection and the following GEMM.
+__global__ void skinny_finalize_norm_kernel(const float* __restrict__ partial, const __nv_bfloat16* __restrict__ R,
+                                            __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ w,
+                                            __nv_bfloat16* __restrict__ aux, int M, int N, int splits, float eps, int kyutai) {
+  __shared__ float red[32];
+  const int m = blockIdx.x;
+  const long long MN = (long long)M * N;
+  float ss = 0.f;
+  for (int n = threadIdx.x * 4; n < N; n += blockDim.x * 4) {
+    const long long i = (long long)m * N + n;
+    float4 v = *reinterpret_cast<const float4*>(partial + i);
+    for (int s = 1; s < splits; ++s) {
+      const float4 t = *reinterpret_cast<const float4*>(partial + (long long)s * MN + i);
+      v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+    }
+    if (R) {
+      const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(R + i);
+      const float2 a = __bfloat1622float2(r2[0]), b = __bfloat1622float2(r2[1]);
+      v.x += a.x; v.y += a.y; v.z += b.x; v.w += b.y;
+    }
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(out + i);
+    o2[0] = lo; o2[1] = hi;
+    const float2 fa = __bfloat1622float2(lo), fb = __bfloat1622float2(hi);  // the norm sees the stored bf16 values
+    ss = fmaf(fa.x, fa.x, ss); ss = fmaf(fa.y, fa.y, ss); ss = fmaf(fb.x, fb.x, ss); ss = fmaf(fb.y, fb.y, ss);
+  }
+  ss = warp_sum(ss);
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = ss;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < blockDim.x / 32 ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) red[0] = t;
+  }
+  __syncthreads();
+  const float mean = red[0] / (float)N;
+  const float r = kyutai ? rsqrtf(eps + mean) : rsqrtf(mean + eps);
+  for (int n = threadIdx.x * 4; n < N; n += blockDim.x * 4) {
+    const long long i = (long long)m * N + n;
+    const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(out + i);
+    const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(w + n);
+    const float2 xa = __bfloat1622float2(x2[0]), xb = __bfloat1622float2(x2[1]);
+    const float2 wa = __bfloat1622float2(w2[0]), wb = __bfloat1622float2(w2[1]);
+    float4 o;
+    if (kyutai) { o.x = xa.x * (wa.x * r); o.y = xa.y * (wa.y * r); o.z = xb.x * (wb.x * r); o.w = xb.y * (wb.y * r); }
+    else        { o.x = (xa.x * r) * wa.x; o.y = (xa.y * r) * wa.y; o.z = (xb.x * r) * wb.x; o.w = (xb.y * r) * wb.y; }
+    __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(aux + i);
+    a2[0] = __floats2bfloat162_rn(o.x, o.y);
+    a2[1] = __floats2bfloat162_rn(o.z, o.w);
+  }
+}
+
+// finalize + SiLU gating: aux[m][c] = bf16(silu(bf16(a)) ) * bf16(b) with a = cols [0,I), b = cols [I,2I) of the GEMM result
+__global__ void skinny_finalize_silu_kernel(const float* __restrict__ partial, __nv_bfloat16* __restrict__ aux, int M, int N,
+                                            int splits) {
+  const int I = N / 2;
+  const long long MN = (long long)M * N, total = (long long)M * I;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / I, c = i % I;
+    float a = 0.f, b = 0.f;
+    for (int s = 0; s < splits; ++s) {
+      a += partial[(long long)s * MN + m * N + c];
+      b += partial[(long long)s * MN + m * N + I + c];
+    }
+    a = __bfloat162float(__float2bfloat16(a));
+    b = __bfloat162float(__float2bfloat16(b));
+    const float sl = __bfloat162float(__float2bfloat16(a / (1.0f + expf(-a))));
+    aux[i] = __float2bfloat16(sl * b);
   }
 }
 
@@ -160,11 +245,31 @@ struct rstnet_skinny_plan {
   SkParams p;
   dim3 grid;
   size_t smem;
+  int fin_mode;  // 0 plain, 1 finalize + residual + RMSNorm -> aux, 2 finalize + SiLU gating -> aux
+  const __nv_bfloat16* norm_w;
+  __nv_bfloat16* aux;
+  float eps;
+  int kyutai;
 };
+
+extern "C" int rstnet_skinny_gemm_create_fused(const void* X, const void* W, const void* R, void* out, float* partial_ws,
+                                               int32_t M, int32_t N, int32_t K, int32_t max_splits, int32_t fin_mode,
+                                               const void* norm_w, void* aux_out, float eps, int32_t kyutai,
+                                               rstnet_skinny_plan** outp);
 
 extern "C" int rstnet_skinny_gemm_create(const void* X, const void* W, const void* R, void* out, float* partial_ws,
                                          int32_t M, int32_t N, int32_t K, int32_t max_splits, rstnet_skinny_plan** outp) {
-  RSTNET_REQUIRE(X && W && out && outp, "skinny_gemm_create: null pointer");
+  return rstnet_skinny_gemm_create_fused(X, W, R, out, partial_ws, M, N, K, max_splits, 0, nullptr, nullptr, 0.f, 0, outp);
+}
+
+extern "C" int rstnet_skinny_gemm_create_fused(const void* X, const void* W, const void* R, void* out, float* partial_ws,
+                                               int32_t M, int32_t N, int32_t K, int32_t max_splits, int32_t fin_mode,
+                                               const void* norm_w, void* aux_out, float eps, int32_t kyutai,
+                                               rstnet_skinny_plan** outp) {
+  RSTNET_REQUIRE(X && W && outp && (out || fin_mode == 2), "skinny_gemm_create: null pointer");
+  RSTNET_REQUIRE(fin_mode >= 0 && fin_mode <= 2, "skinny_gemm_create: bad fin_mode");
+  RSTNET_REQUIRE(fin_mode == 0 || (partial_ws && aux_out && N % 4 == 0 && (fin_mode == 2 || norm_w)),
+                 "skinny_gemm_create: fused finalize needs a workspace, an aux output and N %% 4 == 0");
   RSTNET_REQUIRE(M >= 1 && M <= 128 && N >= 1 && K >= SK_BK && K % SK_BK == 0, "skinny_gemm_create: need 1<=M<=128, K %% 64 == 0 (M=%d N=%d K=%d)", M, N, K);
   RSTNET_REQUIRE((uintptr_t)X % 16 == 0 && (uintptr_t)W % 16 == 0, "skinny_gemm_create: X and W must be 16-byte aligned");
   EncodeTiledFn2 enc = get_encode_fn2();
@@ -174,6 +279,7 @@ extern "C" int rstnet_skinny_gemm_create(const void* X, const void* W, const voi
   const int n_tiles = ceil_div(N, SK_BN);
   const int kchunks = K / SK_BK;
   int splits = 1;
+  RSTNET_REQUIRE(!(partial_ws && max_splits > 1) || N % 4 == 0, "skinny_gemm_create: split-K needs N %% 4 == 0");
   if (partial_ws && max_splits > 1) {
     while (splits < max_splits && n_tiles * splits < 2 * 148 - 40 && kchunks / (splits * 2) >= 8) splits *= 2;
   }
@@ -198,6 +304,9 @@ extern "C" int rstnet_skinny_gemm_create(const void* X, const void* W, const voi
   SkParams& p = pl->p;
   p.out = (__nv_bfloat16*)out; p.partial = partial_ws; p.R = (const __nv_bfloat16*)R;
   p.M = M; p.N = N; p.K = K; p.MB = MB; p.splits = splits;
+  pl->fin_mode = fin_mode; pl->norm_w = (const __nv_bfloat16*)norm_w; pl->aux = (__nv_bfloat16*)aux_out; pl->eps = eps; pl->kyutai = kyutai;
+  // a fused finalize always reads fp32 partials, so the main kernel takes the split path even with one split
+  p.force_partial = fin_mode != 0;
   p.k_iters = ceil_div(kchunks, splits);
   pl->grid = dim3((unsigned)n_tiles, (unsigned)splits);
   const int stage_bytes = SK_W_BYTES + ((MB * 128 + 1023) & ~1023);
@@ -219,9 +328,22 @@ extern "C" int rstnet_skinny_gemm_run(const rstnet_skinny_plan* pl, rstnet_strea
   gemm_skinny_kernel<4><<<pl->grid, SK_THREADS, pl->smem, st>>>(pl->tmW, pl->tmX, pl->p);
   count_launch();
   if (int e = check_launch("gemm_skinny")) return e;
+  const long long MN = (long long)pl->p.M * pl->p.N;
+  if (pl->fin_mode == 1) {
+    skinny_finalize_norm_kernel<<<pl->p.M, 256, 0, st>>>(pl->p.partial, pl->p.R, pl->p.out, pl->norm_w, pl->aux, pl->p.M, pl->p.N,
+                                                         pl->p.splits, pl->eps, pl->kyutai);
+    count_launch();
+    return check_launch("skinny_finalize_norm");
+  }
+  if (pl->fin_mode == 2) {
+    int g = ceil_div(MN / 2, 256);
+    if (g > 148 * 8) g = 148 * 8;
+    skinny_finalize_silu_kernel<<<g, 256, 0, st>>>(pl->p.partial, pl->aux, pl->p.M, pl->p.N, pl->p.splits);
+    count_launch();
+    return check_launch("skinny_finalize_silu");
+  }
   if (pl->p.splits > 1) {
-    const long long MN = (long long)pl->p.M * pl->p.N;
-    int g = ceil_div(MN, 256);
+    int g = ceil_div(MN / 4, 256);
     if (g > 148 * 4) g = 148 * 4;
     skinny_finalize_kernel<<<g, 256, 0, st>>>(pl->p.partial, pl->p.R, pl->p.out, MN, pl->p.splits);
     count_launch();

@@ -65,21 +65,29 @@ class Config:
 
 
 class SkinnyGemm:
-    """rstnet_skinny_gemm_* plan: out[m,n] = sum_k X[m,k] W[n,k] (+ R[m,n]), bf16."""
+    """rstnet_skinny_gemm_* plan: out[m,n] = sum_k X[m,k] W[n,k] (+ R[m,n]), bf16, optionally with a fused finalize:
+    norm_w/aux -> aux = RMSNorm(out) * norm_w (the next GEMM's pre-norm); silu_out -> silu_out = silu(a) * b."""
 
-    def __init__(self, X: torch.Tensor, W: torch.Tensor, out: torch.Tensor, R: Optional[torch.Tensor], ws: Optional[torch.Tensor],
-                 max_splits: int = 8):
+    def __init__(self, X: torch.Tensor, W: torch.Tensor, out: Optional[torch.Tensor], R: Optional[torch.Tensor],
+                 ws: Optional[torch.Tensor], max_splits: int = 8, norm_w: Optional[torch.Tensor] = None,
+                 aux: Optional[torch.Tensor] = None, eps: float = 0.0, kyutai: bool = False, silu_out: Optional[torch.Tensor] = None):
         M, K = X.shape
         N = W.shape[0]
-        assert W.shape[1] == K and out.shape == (M, N) and X.dtype == W.dtype == out.dtype == torch.bfloat16
-        assert X.is_contiguous() and W.is_contiguous() and out.is_contiguous()
-        self._keep = (X, W, out, R, ws)
+        assert W.shape[1] == K and X.dtype == W.dtype == torch.bfloat16 and X.is_contiguous() and W.is_contiguous()
+        if N % 4 != 0:
+            ws = None  # split-K / fused finalize work on 4-element groups
+        mode = 2 if silu_out is not None else (1 if norm_w is not None else 0)
+        if mode and ws is None:
+            raise RstnetError("fused finalize needs a workspace and N % 4 == 0")
+        aux_t = silu_out if mode == 2 else aux
+        self._keep = (X, W, out, R, ws, norm_w, aux_t)
         self._h = C.c_void_p()
         self.flops = 2.0 * M * N * K
         self.bytes = 2.0 * (N * K + M * K + M * N)
-        _lib.check(_lib.lib().rstnet_skinny_gemm_create(X.data_ptr(), W.data_ptr(), None if R is None else R.data_ptr(),
-                                                        out.data_ptr(), None if ws is None else ws.data_ptr(), M, N, K,
-                                                        max_splits if ws is not None else 1, C.byref(self._h)), "skinny_gemm_create")
+        p = lambda t: None if t is None else t.data_ptr()
+        _lib.check(_lib.lib().rstnet_skinny_gemm_create_fused(p(X), p(W), p(R), p(out), p(ws), M, N, K,
+                                                              max_splits if ws is not None else 1, mode, p(norm_w), p(aux_t),
+                                                              float(eps), int(kyutai), C.byref(self._h)), "skinny_gemm_create")
 
     def run(self):
         _lib.check(_lib.lib().rstnet_skinny_gemm_run(self._h, ops._stream()), "skinny_gemm_run")
@@ -349,36 +357,49 @@ class _LMState:
             m._packed = {f"fc12.{l}": torch.cat([P[f"transformer.h.{l}.mlp.fc_1.linear.weight"],
                                                  P[f"transformer.h.{l}.mlp.fc_2.linear.weight"]], 0).contiguous()
                          for l in range(c.n_layer)}
-        G = lambda X, W, out, R=None: SkinnyGemm(X, W, out, R, self.ws if W.shape[0] <= max(3 * E, 2 * I, 4096) else None)
-        self.layers = []
-        for l in range(c.n_layer):
-            p = f"transformer.h.{l}"
-            self.layers.append(dict(
-                n1=P[f"{p}.norm_1.weight"], n2=P[f"{p}.norm_2.weight"],
-                qkv=G(self.xn, P[f"{p}.attn.attn.linear.weight"], self.qkv),
-                proj=G(self.att, P[f"{p}.attn.proj.linear.weight"], self.x, self.x),
-                fc=G(self.xn, m._packed[f"fc12.{l}"], self.ab),
-                down=G(self.hmid, P[f"{p}.mlp.proj.linear.weight"], self.x, self.x)))
+        wsmax = max(3 * E, 2 * I, 4096)
+        G = lambda X, W, out, R=None, **kw: SkinnyGemm(X, W, out, R, self.ws if W.shape[0] <= wsmax else None, **kw)
+        L_ = c.n_layer
+        n1 = [P[f"transformer.h.{l}.norm_1.weight"] for l in range(L_)]
+        n2 = [P[f"transformer.h.{l}.norm_2.weight"] for l in range(L_)]
         self.ln_f = P["transformer.ln_f.weight"]
+        self.n1_first = n1[0]
+        self.layers = []
+        for l in range(L_):
+            p = f"transformer.h.{l}"
+            last = l == L_ - 1
+            self.layers.append(dict(
+                qkv=G(self.xn, P[f"{p}.attn.attn.linear.weight"], self.qkv),
+                # x = attn + x ; xn = norm_2(x)   (Block.forward, llama_streaming.py:846-849) in the GEMM's finalize
+                proj=G(self.att, P[f"{p}.attn.proj.linear.weight"], self.x, self.x, norm_w=n2[l], aux=self.xn, eps=c.norm_eps),
+                # hmid = silu(fc_1 x) * fc_2 x   (LLaMAMLP, lit_model.py:399-403)
+                fc=G(self.xn, m._packed[f"fc12.{l}"], None, silu_out=self.hmid),
+                # x = mlp + x ; xn = norm_1 of the next block (or ln_f -> transformer_out)
+                down=G(self.hmid, P[f"{p}.mlp.proj.linear.weight"], self.x, self.x, norm_w=self.ln_f if last else n1[l + 1],
+                       aux=self.out if last else self.xn, eps=c.norm_eps)))
         self.head = G(self.out, P["lm_head.linear.weight"], self.logits)
         # depth transformer: per-codebook-step weight slabs
         self.text_emb = P["codecformer_text_emb_.weight"]
         self.dep_emb = [P[f"codecformer_emb.{i}.weight"] for i in range(c.dep_q - 1)]
+        Ld = c.codecformer_layers
+        a1 = [P[f"codecformer_.layers.{l}.norm1.alpha"].view(-1) for l in range(Ld)]
+        a2 = [P[f"codecformer_.layers.{l}.norm2.alpha"].view(-1) for l in range(Ld)]
         self.dsteps = []
         for k in range(c.dep_q):
             layers = []
-            for l in range(c.codecformer_layers):
+            for l in range(Ld):
                 p = f"codecformer_.layers.{l}"
                 w_in = P[f"{p}.self_attn.in_proj_weight"].view(c.dep_q, 3 * D, D)[k]
                 w_out = P[f"{p}.self_attn.out_proj.weight"].view(c.dep_q, D, D)[k]
+                nxt = dict(norm_w=a1[l + 1], aux=self.dn, eps=1e-8, kyutai=True) if l + 1 < Ld else {}
                 layers.append(dict(
-                    a1=P[f"{p}.norm1.alpha"].view(-1), a2=P[f"{p}.norm2.alpha"].view(-1),
-                    qkv=G(self.dn, w_in, self.dqkv), out=G(self.datt, w_out, self.dx, self.dx),
-                    gin=G(self.dn, P[f"{p}.gating.{k}.linear_in.weight"], self.dab),
-                    gout=G(self.dh, P[f"{p}.gating.{k}.linear_out.weight"], self.dx, self.dx)))
+                    qkv=G(self.dn, w_in, self.dqkv),
+                    out=G(self.datt, w_out, self.dx, self.dx, norm_w=a2[l], aux=self.dn, eps=1e-8, kyutai=True),
+                    gin=G(self.dn, P[f"{p}.gating.{k}.linear_in.weight"], None, silu_out=self.dh),
+                    gout=G(self.dh, P[f"{p}.gating.{k}.linear_out.weight"], self.dx, self.dx, **nxt)))
             self.dsteps.append(dict(
-                inp=G(self.tout, P[f"codecformer_in.{k}.weight"], self.dx, self.demb), layers=layers,
-                head=G(self.dx, P[f"audio_linears.{k}.weight"], self.dlogits)))
+                inp=G(self.tout, P[f"codecformer_in.{k}.weight"], self.dx, self.demb, norm_w=a1[0], aux=self.dn, eps=1e-8, kyutai=True),
+                layers=layers, head=G(self.dx, P[f"audio_linears.{k}.weight"], self.dlogits)))
         self.depth_step: Optional[int] = None
         self.graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self.warm: Dict[tuple, int] = {}
@@ -396,8 +417,8 @@ class _LMState:
         E = c.n_embd
         _lib.check(L.rstnet_lm_embed_sum_bf16(self.seq.data_ptr(), c.n_q + 1, self.wte.data_ptr(), self.table_ptrs.data_ptr(),
                                               c.n_q, E, self.x.data_ptr(), B, st), "lm_embed_sum")
+        _lib.check(L.rstnet_lm_rms_norm_bf16(self.x.data_ptr(), self.n1_first.data_ptr(), self.xn.data_ptr(), B, E, c.norm_eps, 0, st), "rms")
         for l, ly in enumerate(self.layers):
-            _lib.check(L.rstnet_lm_rms_norm_bf16(self.x.data_ptr(), ly["n1"].data_ptr(), self.xn.data_ptr(), B, E, c.norm_eps, 0, st), "rms")
             ly["qkv"].run()
             _lib.check(L.rstnet_lm_rope_kv_append_bf16(self.qkv.data_ptr(), self.cos.data_ptr(), self.sin.data_ptr(),
                                                        self.offset.data_ptr(), self.q.data_ptr(), self.kv[l].data_ptr(), B,
@@ -405,34 +426,28 @@ class _LMState:
             _lib.check(L.rstnet_lm_ring_decode_attention_bf16(self.q.data_ptr(), self.kv[l].data_ptr(), self.offset.data_ptr(),
                                                               self.att.data_ptr(), B, c.n_head, c.head_size, self.cap, c.context, st),
                        "attention")
-            ly["proj"].run()
-            _lib.check(L.rstnet_lm_rms_norm_bf16(self.x.data_ptr(), ly["n2"].data_ptr(), self.xn.data_ptr(), B, E, c.norm_eps, 0, st), "rms")
-            ly["fc"].run()
-            _lib.check(L.rstnet_lm_silu_mul_bf16(self.ab.data_ptr(), self.hmid.data_ptr(), B, c.intermediate_size, st), "silu_mul")
-            ly["down"].run()
-        _lib.check(L.rstnet_lm_rms_norm_bf16(self.x.data_ptr(), self.ln_f.data_ptr(), self.out.data_ptr(), B, E, c.norm_eps, 0, st), "rms")
+            ly["proj"].run()   # + residual + norm_2 -> xn
+            ly["fc"].run()     # + SiLU gating -> hmid
+            ly["down"].run()   # + residual + next pre-norm -> xn (last layer: ln_f -> transformer_out)
         self.head.run()
         ops.counter_add(self.offset, 1)
 
     def _depth(self, k: int, ids: torch.Tensor, id_stride: int):
         c, B, L = self.c, self.B, _lib.lib()
         st = ops._stream()
-        D, H = c.codecformer_dim, c.ff_hidden
+        D = c.codecformer_dim
         table = self.text_emb if k == 0 else self.dep_emb[k - 1]
         _lib.check(L.rstnet_lm_embed_rows_bf16(ids.data_ptr(), id_stride, table.data_ptr(), D, self.demb.data_ptr(), B, st), "embed_rows")
         ds = self.dsteps[k]
-        ds["inp"].run()
+        ds["inp"].run()        # dx = in_k(transformer_out) + emb ; dn = norm1_0(dx)
         hd = D // c.codecformer_heads
         for l, ly in enumerate(ds["layers"]):
-            _lib.check(L.rstnet_lm_rms_norm_bf16(self.dx.data_ptr(), ly["a1"].data_ptr(), self.dn.data_ptr(), B, D, 1e-8, 1, st), "rms")
             ly["qkv"].run()
             _lib.check(L.rstnet_lm_depth_attention_bf16(self.dqkv.data_ptr(), self.dkv[l].data_ptr(), self.datt.data_ptr(), B,
                                                         c.codecformer_heads, hd, c.dep_q, k, st), "depth_attention")
-            ly["out"].run()
-            _lib.check(L.rstnet_lm_rms_norm_bf16(self.dx.data_ptr(), ly["a2"].data_ptr(), self.dn.data_ptr(), B, D, 1e-8, 1, st), "rms")
-            ly["gin"].run()
-            _lib.check(L.rstnet_lm_silu_mul_bf16(self.dab.data_ptr(), self.dh.data_ptr(), B, H, st), "silu_mul")
-            ly["gout"].run()
+            ly["out"].run()    # dx += out_k(att) ; dn = norm2(dx)
+            ly["gin"].run()    # dh = silu(a) * b
+            ly["gout"].run()   # dx += out(dh) ; dn = norm1 of the next layer
         ds["head"].run()
 
     def _sample(self, logits: torch.Tensor, V: int, n_valid: int, top_k: int, temp: float, col: int, salt: int):
