@@ -174,8 +174,10 @@ def run_ours(args):
     B = STREAMS
     # 10 s of audio per stream: 4 distinct seeded clips tiled over the batch, plus per-rank offset
     base = S.synthetic_audio(8, FRAME * FRAMES, seed=100 + rank)
-    host = base.repeat(B // 8, 1, 1).contiguous().pin_memory()        # [B,1,240000] pinned host
+    host = base.repeat(B // 8, 1, 1).contiguous()                      # [B,1,240000]
     x_dev = host.to(dev)                                               # resident copy for `value`
+    # e2e arm: audio arrives as 80 ms chunks (one per stream per step), each chunk contiguous in pinned host memory
+    host_frames = host.view(B, 1, FRAMES, FRAME).permute(2, 0, 1, 3).contiguous().pin_memory()   # [FRAMES,B,1,1920]
     out_wav_host = torch.empty(B, 1, FRAME, dtype=torch.float32).pin_memory()
     out_codes_host = torch.empty(B, 8, 1, dtype=torch.int64).pin_memory()
 
@@ -191,7 +193,7 @@ def run_ours(args):
             if resident:
                 chunk = x_dev[..., i * FRAME:(i + 1) * FRAME]
             else:
-                chunk = host[..., i * FRAME:(i + 1) * FRAME].to(dev, non_blocking=True)
+                chunk = host_frames[i].to(dev, non_blocking=True)
             codes = m.encode(chunk)
             wav = m.decode(codes)
             if not resident:

@@ -57,6 +57,10 @@ typedef struct {
   int64_t c_batch_stride, c_row_stride;
   int32_t batch, rows, N, K;
   int32_t pre_act, post_act;
+  /* taps > 1: K = taps * kc and tap j of a row starts at A_row + j*tap_stride (a causal conv over the time-major
+   * [T, B, C] layout, where consecutive time steps are B*C elements apart); taps <= 1: K contiguous. */
+  int32_t taps;
+  int64_t tap_stride;
 } rstnet_gemm_rows_args;
 int rstnet_gemm_rows_f32(const rstnet_gemm_rows_args* args, rstnet_stream_t stream);
 

@@ -34,7 +34,7 @@ class GemmRowsArgs(C.Structure):
         ("R", C.c_void_p), ("r_batch_stride", C.c_int64), ("r_row_stride", C.c_int64),
         ("C", C.c_void_p), ("c_batch_stride", C.c_int64), ("c_row_stride", C.c_int64),
         ("batch", C.c_int32), ("rows", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
-        ("pre_act", C.c_int32), ("post_act", C.c_int32),
+        ("pre_act", C.c_int32), ("post_act", C.c_int32), ("taps", C.c_int32), ("tap_stride", C.c_int64),
     ]
 
 

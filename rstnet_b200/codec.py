@@ -484,7 +484,7 @@ class _Plan:
     # ---- conv / transposed conv over a _Buf (taps along time)
     def conv(self, A: _Buf, a_row0: int, stride: int, pack, out: _Buf, out_row0: int, T_out: int, *, pre=ACT_NONE,
              post=ACT_NONE, R: Optional[_Buf] = None, r_row0: int = 0, tr_stride: int = 0, out2: Optional[_Buf] = None,
-             out2_row0: int = 0):
+             out2_row0: int = 0, ffma: bool = False):
         """out2 (tensor-core plans only): ELU'd copy of the raw output, written by the same epilogue, so the
         consumer that needs a pre-activation (resblock conv1) does not re-apply ELU per tap and per N tile."""
         B, Cin = self.B, A.C
@@ -496,6 +496,17 @@ class _Plan:
                 kw.update(R=R.t, r_off=R.off(r_row0), r_bs=R.bs, r_rs=R.ts)
             self.add(lambda: ops.gemm_rows(A.t, A.off(a_row0), A.bs, stride * Cin, pack["Wt"], out.t, out.off(out_row0),
                                            out.bs, N, B, T_out, **kw))
+            return
+        if ffma:
+            # time-major layout on the CUDA cores: rows of a "batch" = the B streams of one output time step, taps are
+            # B*Cin apart.  Measured faster than the tensor-core kernel for the small-K resblock convs (launch lists
+            # profiles/r1_*): those are HBM / latency bound and the 3xTF32 pipeline's per-tile cost dominates.
+            assert not tr_stride and out2 is None
+            kw = dict(bias=pack["bias"], pre_act=pre, post_act=post, taps=taps, tap_stride=B * Cin)
+            if R is not None:
+                kw.update(R=R.t, r_off=R.off(r_row0), r_bs=B * R.C, r_rs=R.C)
+            self.add(lambda: ops.gemm_rows(A.t, A.off(a_row0), stride * B * Cin, Cin, pack["Wt"], out.t, out.off(out_row0),
+                                           B * out.C, out.C, T_out, B, **kw))
             return
         kw = dict(taps=taps, tap_do=1, o_mul=stride, bias=pack["bias"], pre_act=pre, post_act=post, precision=self.precision)
         if R is not None:
@@ -645,8 +656,8 @@ class _EncPlan(_Plan):
         for i, ratio in enumerate(eng.enc_ratios):
             w1, w2 = eng.e_res[i]
             # SEANetResnetBlock: ELU -> k3 -> ELU -> k1, + skip; the ELU that follows is fused as post_act
-            self.conv(ya[i], 0, 1, w1, h[i], 0, T[i], pre=ACT_NONE if self.tc else ACT_ELU, post=ACT_ELU)
-            self.conv(h[i], 0, 1, w2, r_[i], r_[i].ctx, T[i], post=ACT_ELU, R=y[i], r_row0=y[i].ctx)
+            self.conv(ya[i], 0, 1, w1, h[i], 0, T[i], pre=ACT_NONE if self.tc else ACT_ELU, post=ACT_ELU, ffma=self.tc)
+            self.conv(h[i], 0, 1, w2, r_[i], r_[i].ctx, T[i], post=ACT_ELU, R=y[i], r_row0=y[i].ctx, ffma=self.tc)
             if i + 1 < len(y):
                 nxt = y[i + 1]
                 self.conv(r_[i], 0, ratio, eng.e_down[i], nxt, nxt.ctx, T[i + 1],
@@ -734,8 +745,8 @@ class _DecPlan(_Plan):
                       out2_row0=yda[i].ctx)
             Tout = Tin * r
             w1, w2 = eng.d_res[i]
-            self.conv(yda[i], 0, 1, w1, hd_[i], 0, Tout, pre=ACT_NONE if self.tc else ACT_ELU, post=ACT_ELU)
-            self.conv(hd_[i], 0, 1, w2, a[i + 1], a[i + 1].ctx, Tout, post=ACT_ELU, R=yd[i], r_row0=yd[i].ctx)
+            self.conv(yda[i], 0, 1, w1, hd_[i], 0, Tout, pre=ACT_NONE if self.tc else ACT_ELU, post=ACT_ELU, ffma=self.tc)
+            self.conv(hd_[i], 0, 1, w2, a[i + 1], a[i + 1].ctx, Tout, post=ACT_ELU, R=yd[i], r_row0=yd[i].ctx, ffma=self.tc)
             Tin = Tout
         last = a[-1]
         self.add(lambda: ops.conv1d_cout1(last.t, last.bs, last.ts, eng.d_final_w, eng.d_final_b, wav, Lout, B, Lout, last.C,

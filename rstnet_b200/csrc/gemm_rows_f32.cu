@@ -42,6 +42,8 @@ __global__ void __launch_bounds__(Cfg::NT) gemm_rows_kernel(const rstnet_gemm_ro
   const long long m0 = (long long)blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
   const int K = p.K, N = p.N;
+  const int kc = p.taps > 1 ? p.K / p.taps : p.K;
+  const long long tap_stride = p.taps > 1 ? p.tap_stride : 0;
 
   // ---- per-thread copy assignments (fixed across k tiles)
   const float* a_src[Cfg::A_PER_T];
@@ -55,7 +57,7 @@ __global__ void __launch_bounds__(Cfg::NT) gemm_rows_kernel(const rstnet_gemm_ro
     long long m = m0 + row;
     if (m >= M) m = M - 1;
     long long b = m / p.rows, t = m % p.rows;
-    a_src[i] = p.A + b * p.a_batch_stride + t * p.a_row_stride + 4 * q;
+    a_src[i] = p.A + b * p.a_batch_stride + t * p.a_row_stride;
     a_dst[i] = row * AS + 4 * q;
     a_q[i] = q;
   }
@@ -84,7 +86,10 @@ __global__ void __launch_bounds__(Cfg::NT) gemm_rows_kernel(const rstnet_gemm_ro
       if (tid + i * NT < Cfg::A_CHUNKS) {
         int kk = k0 + 4 * a_q[i];
         bool ok = kk < K;
-        cp_async16(as + a_dst[i], ok ? (const void*)(a_src[i] + k0) : (const void*)p.A, ok ? 16 : 0);
+        // K index -> (tap, channel): taps are tap_stride elements apart (time-major layout); a 4-float
+        // chunk never straddles taps because kc % 4 == 0
+        const int tap = kk / kc, c = kk - tap * kc;
+        cp_async16(as + a_dst[i], ok ? (const void*)(a_src[i] + (long long)tap * tap_stride + c) : (const void*)p.A, ok ? 16 : 0);
       }
     }
 #pragma unroll
@@ -222,6 +227,8 @@ extern "C" int rstnet_gemm_rows_f32(const rstnet_gemm_rows_args* args, rstnet_st
   RSTNET_REQUIRE(a.batch > 0 && a.rows > 0 && a.N > 0 && a.K > 0, "gemm_rows: empty problem (batch=%d rows=%d N=%d K=%d)",
                  a.batch, a.rows, a.N, a.K);
   RSTNET_REQUIRE(a.K % 4 == 0 && a.N % 4 == 0, "gemm_rows: K (%d) and N (%d) must be multiples of 4", a.K, a.N);
+  RSTNET_REQUIRE(a.taps <= 1 || (a.K % a.taps == 0 && (a.K / a.taps) % 4 == 0 && a.tap_stride % 4 == 0),
+                 "gemm_rows: with taps, K/taps and tap_stride must be multiples of 4");
   RSTNET_REQUIRE(a.a_batch_stride % 4 == 0 && a.a_row_stride % 4 == 0 && a.c_batch_stride % 4 == 0 &&
                      a.c_row_stride % 4 == 0 && a.r_batch_stride % 4 == 0 && a.r_row_stride % 4 == 0,
                  "gemm_rows: strides must be multiples of 4 elements (16-byte rows)");

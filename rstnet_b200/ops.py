@@ -31,7 +31,8 @@ def _cuda(*ts):
 
 def gemm_rows(A: torch.Tensor, a_off: int, a_bs: int, a_rs: int, Wt: torch.Tensor, C_: torch.Tensor, c_off: int,
               c_bs: int, c_rs: int, batch: int, rows: int, *, bias=None, scale=None, R=None, r_off: int = 0,
-              r_bs: int = 0, r_rs: int = 0, pre_act: int = ACT_NONE, post_act: int = ACT_NONE) -> None:
+              r_bs: int = 0, r_rs: int = 0, pre_act: int = ACT_NONE, post_act: int = ACT_NONE, taps: int = 1,
+              tap_stride: int = 0) -> None:
     """C[b,t,:] = post(R + scale*(pre(A_row(b,t)) @ Wt + bias)); offsets/strides in elements."""
     _cuda(A, Wt, C_, bias, scale, R)
     K, N = Wt.shape
@@ -46,6 +47,7 @@ def gemm_rows(A: torch.Tensor, a_off: int, a_bs: int, a_rs: int, Wt: torch.Tenso
     a.c_batch_stride, a.c_row_stride = c_bs, c_rs
     a.batch, a.rows, a.N, a.K = batch, rows, N, K
     a.pre_act, a.post_act = pre_act, post_act
+    a.taps, a.tap_stride = taps, tap_stride
     _lib.check(_lib.lib().rstnet_gemm_rows_f32(C.byref(a), _stream()), "gemm_rows_f32")
 
 
