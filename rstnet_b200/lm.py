@@ -302,7 +302,7 @@ class GPT(nn.Module):
 
     @torch.no_grad()
     def forward_step(self, sequence: torch.Tensor, *, use_sampling: bool = True, temp_text: float = 0.7, top_k_text: int = 25,
-                     temp: float = 0.8, top_k: int = 30, audio_valid: int = 2049) -> torch.Tensor:
+                     temp: float = 0.8, top_k: int = 30, audio_valid=2049) -> torch.Tensor:
         """One generated frame: temporal step on sequence[B,9,1], text token, then the 8 depth steps, each sampled
         on the device (sample_token / sample_token_audio, utils/sampling.py:85-154).  Returns tokens [B, 9]
         (text, audio_0..7).  With use_cuda_graphs the whole frame is a single graph replay."""
@@ -503,8 +503,9 @@ class _LMState:
             self.tout.copy_(ops_t)
             for k in range(c.dep_q):
                 self._depth(k, self.tokens[:, k], c.dep_q + 1)
-                self._sample(self.dlogits, c.audio_card, min(audio_valid, c.audio_card), tk, temp, k + 1, k + 1)
+                av = audio_valid[k] if isinstance(audio_valid, (tuple, list)) else audio_valid
+                self._sample(self.dlogits, c.audio_card, min(av, c.audio_card), tk, temp, k + 1, k + 1)
             ops.counter_add(self.frame_counter, 1)
 
-        self._replay(("frame", tk_text, float(temp_text), tk, float(temp), audio_valid), frame)
+        self._replay(("frame", tk_text, float(temp_text), tk, float(temp), tuple(audio_valid) if isinstance(audio_valid, (tuple, list)) else audio_valid), frame)
         return self.tokens.clone()

