@@ -154,7 +154,11 @@ class MimiCodec(nn.Module):
         # streaming steps run their GEMMs on the tensor cores (tcgen05, 3xTF32 = fp32-equivalent products,
         # fp32 accumulation); False selects the fp32 FFMA kernels (bit-faithful fp32 arithmetic) there too.
         self.streaming_tensor_cores = True
-        self.tc_precision = 0  # 0: 3xTF32, 1: single TF32 pass
+        # 0 = 3xTF32 (fp32-equivalent; the default on both sides: RVQ indices must match the fp32 reference and the
+        # measured waveform error stays at 4e-6).  decoder_precision = 1 opts the decoder into single-pass TF32 (the
+        # precision of PyTorch's own cuDNN convolutions on GPUs): +8 % frames/s, waveform error 1.3e-3 of a 0.57 peak.
+        self.tc_precision = 0
+        self.decoder_precision = 0
 
     # ------------------------------------------------------------------ parameters
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
@@ -462,7 +466,7 @@ class _Plan:
         self.eng, self.B, self.streaming, self.tc = eng, B, streaming, tensor_cores
         self.ops_list = []
         self.graph: Optional[torch.cuda.CUDAGraph] = None
-        self.precision = eng.m.tc_precision
+        self.precision = eng.m.decoder_precision if isinstance(self, _DecPlan) else eng.m.tc_precision
 
     def buf(self, ctx, T, extra, C) -> _Buf:
         return _Buf(self.B, ctx, T, extra, C, self.eng.device, self.tc)

@@ -91,6 +91,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int i0 = it * TC_BM, n0 = blockIdx.y * BN;
   const int total_k = p.taps * p.kchunks;
   const int nchunks = (total_k + CH - 1) / CH;
+  // single-pass TF32 without a pre-activation needs no operand transform: the tensor core reads the top 19 bits
+  // of the fp32 words TMA delivered (truncation), so the MMA warp consumes the TMA barrier directly
+  const bool xf = Cfg::SPLIT || p.pre_act != ACT_NONE;
 
   auto a_hi = [&](int s) { return smem + s * Cfg::STAGE_BYTES; };
   auto b_hi = [&](int s) { return smem + s * Cfg::STAGE_BYTES + TC_A_BYTES; };
@@ -145,7 +148,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t ph = (kit / S) & 1;
       const int chunk = kit / CH, pos = kit % CH, buf = chunk & 1;
       if (pos == 0) mbar_wait(&acc_empty[buf], ((chunk >> 1) & 1) ^ 1);
-      mbar_wait(&ready[s], ph);
+      mbar_wait(xf ? &ready[s] : &full[s], ph);
       tc_fence_after();
       if (elect_one()) {
         if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) p.trace[kit * 8 + 3] = clock64();
@@ -179,7 +182,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ================= transform warps (2..9): pre-activation + TF32 hi/lo split of the A tile, in place.
     // Weights were rounded / split once on the host side of the plan (W_hi, W_lo arrive by TMA).
     const int tid = threadIdx.x - 64;  // 0..255
-    for (int kit = 0; kit < total_k; ++kit) {
+    for (int kit = 0; xf && kit < total_k; ++kit) {
       const int s = kit % S;
       const uint32_t ph = (kit / S) & 1;
       mbar_wait(&full[s], ph);
