@@ -14,6 +14,9 @@
 // hi = rna_tf32(x) and lo = rna_tf32(x - hi) (both exactly representable in TF32), and three TF32
 // MMAs accumulate a_lo*b_hi + a_hi*b_lo + a_hi*b_hi in fp32 (dropping the 2^-22 lo*lo term).
 // Precision 1: one TF32 MMA (hi only).  The transform warps also apply a fused pre-activation (ELU).
+#include <cstdlib>
+#include <type_traits>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "../../include/rstnet_b200.h"
@@ -43,6 +46,7 @@ struct TcParams {
   int I_out, O_out, N, Kc;
   int taps, tap_di, tap_do, o_mul, kchunks;
   int pre_act, post_act, i_tiles;
+  int m_tiles, n_tiles;  // (I tiles x O_out) and N tiles: the persistent .ts kernel walks m_tiles * n_tiles
   long long* trace;  // optional [total_k][8] clock64 stamps of CTA 0 (debug / profiling)
   long long* cta_times;  // optional [grid.x][4] %globaltimer: entry, setup done, mainloop+epilogue done, exit (blockIdx.y == 0)
 };
@@ -280,6 +284,304 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (timed) p.cta_times[blockIdx.x * 4 + 3] = gtime();
 }
 
+// ---------------------------------------------------------------- ".ts" variant: A operand from TMEM, persistent CTAs
+// The SS kernel above is shared-memory-bandwidth bound: per 32-element K stage the hi/lo split writes 32 KB back to
+// shared memory and the three MMAs re-read the A tile three times (~150 KB of smem traffic per 384 clk of MMA work).
+// Here the transform warps read the TMA-landed fp32 A tile ONCE (un-swizzling the 128-byte rows) and write hi / lo
+// straight into TMEM (tcgen05.st), from where tcgen05.mma takes its A operand; only the pre-split weight tiles are
+// read from shared memory by the tensor core.  TMEM: columns [0, 4*BN) two ping-pong buffers of two accumulators,
+// then TS_NA stages of (32 hi + 32 lo) A columns.
+// One CTA per SM walks tiles t = blockIdx.x, +gridDim.x, ... (N tile fastest, so CTAs running together share A rows
+// in L2); the barrier phases run on across tiles, and because the drain warps keep the promoted sums in registers
+// the epilogue of tile t overlaps the MMAs of tile t+1.
+constexpr int TS_NA = 4;
+
+template <int BN>
+struct TsCfg {
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = TC_A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = BN == 64 ? 5 : 6;
+  static constexpr int OUT_LD = BN + 4;                       // padded row of the epilogue staging tile (floats)
+  static constexpr int OUT_BYTES = 4 * 32 * OUT_LD * 4;       // one 32-row slab per drain warp
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/ + 4 * BN * 4 /*bias+scale x2*/ + OUT_BYTES;
+  static constexpr int ACC_COLS = 2 * TC_NACC * BN;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW3, const TcParams p) {
+  using Cfg = TsCfg<BN>;
+  constexpr int S = Cfg::STAGES;
+  constexpr int CH = TC_CHUNK_STAGES;
+  static_assert(CH == 4 && TS_NA == 4, "the static chunk schedule assumes 4 stages per chunk and 4 TMEM A stages");
+  // chunk variants: chunk c of this CTA's stream uses smem stages (4c + u) % S, u = 0..3; the pattern repeats every NV
+  // chunks, and because each smem stage is then used an even number of times per period its mbarrier parity depends
+  // only on (variant, u)
+  constexpr int NV = S / (S % 4 == 0 ? 4 : (S % 2 == 0 ? 2 : 1));
+  static_assert(((4 * NV / S) & 1) == 0, "stage parity must be static");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;                         // [S] TMA landed (A fp32, [B_hi; B_lo])
+  uint64_t* empty = bars + S;                    // [S] MMAs reading B of the stage retired (A smem was consumed earlier)
+  uint64_t* a_ready = bars + 2 * S;              // [NA] hi/lo of the A tile are in TMEM (128 arrivals)
+  uint64_t* a_free = bars + 2 * S + TS_NA;       // [NA] MMAs reading that TMEM stage retired
+  uint64_t* acc_full = bars + 2 * S + 2 * TS_NA; // [2]
+  uint64_t* acc_empty = acc_full + 2;            // [2] (128 arrivals)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* sbs = reinterpret_cast<float*>(smem + S * Cfg::STAGE_BYTES + 512);  // [2][2*BN] bias | scale of the drain's tile
+  float* out_stage = sbs + 4 * BN;                                            // [4 warps][32][OUT_LD] epilogue transpose
+
+  auto gtime = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (long long)t; };
+  const bool timed = p.cta_times && threadIdx.x == 0;
+  const bool tr = p.trace && blockIdx.x == 0;
+  if (timed) p.cta_times[blockIdx.x * 4 + 0] = gtime();
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int total_k = p.taps * p.kchunks;   // multiple of 4 (host-checked)
+  const int nchunks = total_k / CH;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW3);
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < TS_NA; ++s) { mbar_init(&a_ready[s], 128); mbar_init(&a_free[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t a_tmem0 = tmem_base + (uint32_t)Cfg::ACC_COLS;
+  if (timed) p.cta_times[blockIdx.x * 4 + 1] = gtime();
+
+  if (warp == 0) {
+    // ---- TMA producer: one elected thread runs a whole 4-stage chunk with compile-time stage slots
+    int kc = 0, ci = 0, co = 0, n0 = 0, kit = 0;
+    bool first_tile = true;
+    auto chunk = [&](auto vtag) {
+      constexpr int V = decltype(vtag)::value;
+      if (elect_one()) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int s = (4 * V + u) % S;
+          const uint32_t par = (uint32_t)(((4 * V + u) / S) & 1);
+          mbar_wait(&empty[s], par ^ 1);
+          if (tr && first_tile) p.trace[(kit + u) * 8 + 0] = clock64();
+          uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[s], TC_A_BYTES + 2 * Cfg::B_BYTES);
+          tma_load_3d(st, &tmA, &full[s], kc * TC_BKE, ci, co);
+          tma_load_3d(st + TC_A_BYTES, &tmW3, &full[s], (kit + u) * TC_BKE, n0, 0);   // tap * Kc + kc * 32 == kit * 32
+          if (++kc == p.kchunks) { kc = 0; ci += p.tap_di; co += p.tap_do; }
+        }
+      }
+      __syncwarp();
+    };
+    int v = 0;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const int t = blockIdx.x + ti * gridDim.x;
+      const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+      n0 = nt * BN; ci = (mt % p.i_tiles) * TC_BM; co = (mt / p.i_tiles) * p.o_mul; kc = 0;
+      first_tile = ti == 0;
+      for (kit = 0; kit < total_k; kit += 4) {
+        switch (v) {
+          case 0: chunk(std::integral_constant<int, 0>{}); break;
+          case 1: chunk(std::integral_constant<int, 1 % NV>{}); break;
+          case 2: chunk(std::integral_constant<int, 2 % NV>{}); break;
+          case 3: chunk(std::integral_constant<int, 3 % NV>{}); break;
+          default: chunk(std::integral_constant<int, 4 % NV>{}); break;
+        }
+        if (++v == NV) v = 0;
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issue: per k-step  D[hh | hl] (+)= A_hi x [B_hi; B_lo]  (one N = 2*BN MMA), then  D[hl] += A_lo x B_hi
+    constexpr uint32_t idesc2 = instr_desc(2u, TC_BM, 2 * BN), idesc1 = instr_desc(2u, TC_BM, BN);
+    const uint64_t desc0 = smem_desc_sw128(smem_u32(smem));   // stage s adds s * STAGE_BYTES / 16 to the address field
+    int cc = 0, kit = 0;
+    bool first_tile = true;
+    auto chunk = [&](auto vtag) {
+      constexpr int V = decltype(vtag)::value;
+      if (elect_one()) {
+        const int buf = cc & 1;
+        const uint32_t pa = (uint32_t)(cc & 1);
+        mbar_wait(&acc_empty[buf], (uint32_t)(((cc >> 1) & 1) ^ 1));
+        const uint32_t d0 = tmem_base + (uint32_t)(buf * TC_NACC * BN), d1 = d0 + (uint32_t)BN;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int s = (4 * V + u) % S;
+          mbar_wait(&a_ready[u], pa);   // implies full[s]: the transform waited for it
+          tc_fence_after();
+          if (tr && first_tile) p.trace[(kit + u) * 8 + 3] = clock64();
+          const uint32_t ah = a_tmem0 + (uint32_t)(u * 64), al = ah + 32u;
+          const uint64_t db = desc0 + (uint64_t)((s * Cfg::STAGE_BYTES + TC_A_BYTES) >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            mma_tf32_ts(d0, ah + (uint32_t)(8 * k), db + (uint64_t)(2 * k), idesc2, (u == 0 && k == 0) ? 0u : 1u);
+            mma_tf32_ts(d1, al + (uint32_t)(8 * k), db + (uint64_t)(2 * k), idesc1, 1u);
+          }
+          tc_commit(&empty[s]);
+          tc_commit(&a_free[u]);
+          if (u == 3) tc_commit(&acc_full[buf]);
+          if (tr && first_tile) p.trace[(kit + u) * 8 + 4] = clock64();
+        }
+      }
+      __syncwarp();
+    };
+    int v = 0;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      first_tile = ti == 0;
+      for (kit = 0; kit < total_k; kit += 4, ++cc) {
+        switch (v) {
+          case 0: chunk(std::integral_constant<int, 0>{}); break;
+          case 1: chunk(std::integral_constant<int, 1 % NV>{}); break;
+          case 2: chunk(std::integral_constant<int, 2 % NV>{}); break;
+          case 3: chunk(std::integral_constant<int, 3 % NV>{}); break;
+          default: chunk(std::integral_constant<int, 4 % NV>{}); break;
+        }
+        if (++v == NV) v = 0;
+      }
+    }
+  } else if (warp < 10) {
+    // transform: two groups of 4 warps alternate stages; thread = one A row (TMEM lane).  It never looks at tile
+    // boundaries: stage g of this CTA's stream is stage g, whatever tile it belongs to.
+    const int grp = (warp - 2) / 4, q = warp % 4;
+    const int row = q * 32 + lane;
+    const uint32_t rowoff = (uint32_t)(row * 128 + ((row & 7) << 4));   // chunk j of the swizzled row: rowoff ^ (j << 4)
+    const uint32_t smem0 = smem_u32(smem);
+    const uint32_t ta0 = a_tmem0 + ((uint32_t)(q * 32) << 16);
+    const int my_total = my_tiles * total_k;
+    auto run = [&](auto act_tag) {
+      constexpr bool ACT = decltype(act_tag)::value;
+      for (int g = grp; g < my_total; g += 2) {
+        const int s = g % S, sa = g % TS_NA;
+        mbar_wait(&full[s], (g / S) & 1);
+        if (tr && q == 0 && lane == 0 && g < total_k) p.trace[g * 8 + 1] = clock64();
+        mbar_wait(&a_free[sa], ((g / TS_NA) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t base = smem0 + (uint32_t)(s * Cfg::STAGE_BYTES) + rowoff;
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 v = lds128(base ^ (uint32_t)(j << 4));
+          if (ACT) {
+            v.x = apply_act(v.x, p.pre_act); v.y = apply_act(v.y, p.pre_act);
+            v.z = apply_act(v.z, p.pre_act); v.w = apply_act(v.w, p.pre_act);
+          }
+          const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t h = (__float_as_uint(e[c]) + 0x1000u) & 0xFFFFE000u;
+            hi[4 * j + c] = h;
+            // the tensor core ignores the low 13 bits of a tf32 operand: adding half an ulp is the whole rounding
+            lo[4 * j + c] = __float_as_uint(e[c] - __uint_as_float(h)) + 0x1000u;
+          }
+        }
+        tmem_st32(ta0 + (uint32_t)(sa * 64), hi);
+        tmem_st32(ta0 + (uint32_t)(sa * 64) + 32u, lo);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&a_ready[sa]);
+        if (tr && q == 0 && lane == 0 && g < total_k) p.trace[g * 8 + 2] = clock64();
+      }
+    };
+    if (p.pre_act != ACT_NONE) run(std::true_type{}); else run(std::false_type{});
+  } else {
+    const int q = warp % 4, dt = threadIdx.x - 320;
+    int cc = 0;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const int t = blockIdx.x + ti * gridDim.x;
+      const int nt = t % p.n_tiles, mt = t / p.n_tiles;
+      const int i0 = (mt % p.i_tiles) * TC_BM, ot = mt / p.i_tiles, n0 = nt * BN;
+      float* sb = sbs + (ti & 1) * 2 * BN;
+      if (dt < BN) sb[dt] = (p.bias && n0 + dt < p.N) ? p.bias[n0 + dt] : 0.f;
+      else if (dt < 2 * BN) sb[dt] = (p.scale && n0 + dt - BN < p.N) ? p.scale[n0 + dt - BN] : 1.f;
+      float acc[BN];
+#pragma unroll
+      for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+      for (int chunk = 0; chunk < nchunks; ++chunk, ++cc) {
+        const int buf = cc & 1;
+        mbar_wait(&acc_full[buf], (cc >> 1) & 1);
+        tc_fence_after();
+        if (tr && ti == 0 && threadIdx.x == 320) p.trace[chunk * 8 + 5] = clock64();
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          uint32_t r[16], r2[16];
+          const uint32_t col = (uint32_t)(buf * TC_NACC * BN + c0);
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + col, r);
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + col + (uint32_t)BN, r2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(r[j]) + __uint_as_float(r2[j]);
+        }
+        tc_fence_before();
+        mbar_arrive(&acc_empty[buf]);
+        if (tr && ti == 0 && threadIdx.x == 320) p.trace[chunk * 8 + 6] = clock64();
+      }
+      named_bar_sync(1, 128);   // bias/scale of this tile are in smem (written before the chunk loop)
+      // transpose through shared memory: thread = row while draining TMEM, 8 lanes = one 128-byte row segment when
+      // storing, so every global access is a full line
+      constexpr int LD = Cfg::OUT_LD;
+      float* stg = out_stage + q * 32 * LD;
+      __syncwarp();
+#pragma unroll
+      for (int g4 = 0; g4 < BN / 4; ++g4)
+        *reinterpret_cast<float4*>(stg + lane * LD + 4 * g4) = make_float4(acc[4 * g4], acc[4 * g4 + 1], acc[4 * g4 + 2], acc[4 * g4 + 3]);
+      __syncwarp();
+      const int cg = lane & 7, rsub = lane >> 3;
+      const long long c_base = (long long)ot * p.c_o_stride, r_base = (long long)ot * p.r_o_stride;
+      const int irow0 = i0 + q * 32 + rsub;
+#pragma unroll
+      for (int pass = 0; pass < BN / 32; ++pass) {
+        const int nl = pass * 32 + cg * 4, n = n0 + nl;
+        if (n < p.N) {
+          const float4 bb = *reinterpret_cast<const float4*>(sb + nl);
+          const float4 ss = *reinterpret_cast<const float4*>(sb + BN + nl);
+          long long coff = n, roff = n;
+          if (p.n_split > 0) {
+            const int j = n / p.n_split, co = n % p.n_split;
+            coff = (long long)j * p.c_split_stride + co;
+            roff = (long long)j * p.r_split_stride + co;
+          }
+          float4 rr[8];
+          if (p.R) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int i = irow0 + 4 * it;
+              rr[it] = i < p.I_out ? __ldg(reinterpret_cast<const float4*>(p.R + r_base + (long long)i * p.r_i_stride + roff)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int i = irow0 + 4 * it;
+            if (i < p.I_out) {
+              float4 v = *reinterpret_cast<const float4*>(stg + (rsub + 4 * it) * LD + nl);
+              v.x = (v.x + bb.x) * ss.x; v.y = (v.y + bb.y) * ss.y; v.z = (v.z + bb.z) * ss.z; v.w = (v.w + bb.w) * ss.w;
+              if (p.R) { v.x += rr[it].x; v.y += rr[it].y; v.z += rr[it].z; v.w += rr[it].w; }
+              const long long off = c_base + (long long)i * p.c_i_stride + coff;
+              if (p.C2)
+                *reinterpret_cast<float4*>(p.C2 + off) = make_float4(apply_act(v.x, p.act2), apply_act(v.y, p.act2), apply_act(v.z, p.act2), apply_act(v.w, p.act2));
+              if (p.post_act != ACT_NONE) {
+                v.x = apply_act(v.x, p.post_act); v.y = apply_act(v.y, p.post_act);
+                v.z = apply_act(v.z, p.post_act); v.w = apply_act(v.w, p.post_act);
+              }
+              *reinterpret_cast<float4*>(p.C + off) = v;
+            }
+          }
+        }
+      }
+    }
+  }
+  if (timed) p.cta_times[blockIdx.x * 4 + 2] = gtime();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if (timed) p.cta_times[blockIdx.x * 4 + 3] = gtime();
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -300,10 +602,26 @@ using namespace rstnet;
 
 struct rstnet_tc_plan {
   CUtensorMap tmA, tmW, tmWlo;
+  CUtensorMap tmW3;  // [2 (hi, lo)][N][K] when W_lo follows W at a 16-byte-aligned distance (.ts kernel)
+  bool ts_ok;
   TcParams p;
-  dim3 grid;
+  dim3 grid;     // one CTA per tile (SS kernel)
+  dim3 grid_ts;  // persistent .ts kernel: min(tiles, SMs)
   int bn, prec;
 };
+
+template <int BN>
+static int tc_launch_ts(const rstnet_tc_plan* pl, cudaStream_t st) {
+  using Cfg = TsCfg<BN>;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(gemm_tc_ts_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    attr = true;
+  }
+  gemm_tc_ts_kernel<BN><<<pl->grid_ts, TC_THREADS, Cfg::SMEM_BYTES, st>>>(pl->tmA, pl->tmW3, pl->p);
+  count_launch();
+  return check_launch("gemm_tc_ts");
+}
 
 template <int BN, int PREC>
 static int tc_launch(const rstnet_tc_plan* pl, cudaStream_t st) {
@@ -369,6 +687,18 @@ extern "C" int rstnet_tc_gemm_create(const rstnet_tc_gemm_desc* d, rstnet_tc_pla
       set_error("tc_gemm_create: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
       return 3;
     }
+    // persistent .ts kernel: 3xTF32 with whole 4-stage chunks and hi/lo weights reachable through one descriptor
+    pl->ts_ok = false;
+    const long long wdiff = d->W_lo ? (const char*)d->W_lo - (const char*)d->W : 0;
+    if (pl->prec == 0 && wdiff > 0 && wdiff % 16 == 0 && (d->taps * (d->Kc / TC_BKE)) % TC_CHUNK_STAGES == 0) {
+      cuuint64_t gdim3[3] = {(cuuint64_t)d->taps * d->Kc, (cuuint64_t)N, 2};
+      cuuint64_t gstr3[2] = {(cuuint64_t)d->taps * d->Kc * 4, (cuuint64_t)wdiff};
+      cuuint32_t box3[3] = {TC_BKE, (cuuint32_t)pl->bn, 2};
+      cuuint32_t estr3[3] = {1, 1, 1};
+      r = enc(&pl->tmW3, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)d->W, gdim3, gstr3, box3, estr3, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      pl->ts_ok = r == CUDA_SUCCESS;
+    }
   }
   TcParams& p = pl->p;
   p.C2 = d->C2; p.act2 = d->act2;
@@ -381,6 +711,13 @@ extern "C" int rstnet_tc_gemm_create(const rstnet_tc_gemm_desc* d, rstnet_tc_pla
   p.trace = nullptr;
   p.cta_times = nullptr;
   pl->grid = dim3((unsigned)(i_tiles * d->O_out), (unsigned)ceil_div(N, pl->bn));
+  p.m_tiles = (int)pl->grid.x; p.n_tiles = (int)pl->grid.y;
+  {
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    const long long tiles = (long long)p.m_tiles * p.n_tiles;
+    pl->grid_ts = dim3((unsigned)(tiles < sms ? tiles : sms));
+  }
   *out = pl;
   return 0;
 }
@@ -389,6 +726,8 @@ extern "C" int rstnet_tc_gemm_run(const rstnet_tc_plan* pl, rstnet_stream_t stre
   RSTNET_REQUIRE(pl != nullptr, "tc_gemm_run: null plan");
   cudaStream_t st = (cudaStream_t)stream;
   if (pl->prec == 0) {
+    static const bool use_ts = []() { const char* e = getenv("RSTNET_TC_SS"); return !(e && e[0] == '1'); }();
+    if (use_ts && pl->ts_ok) return pl->bn == 64 ? tc_launch_ts<64>(pl, st) : tc_launch_ts<32>(pl, st);
     if (pl->bn == 64) return tc_launch<64, 0>(pl, st);
     return tc_launch<32, 0>(pl, st);
   }

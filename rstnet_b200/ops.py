@@ -55,7 +55,8 @@ def tf32_split(w: torch.Tensor):
     """(hi, lo) with hi = tf32_rna(w), lo = tf32_rna(w - hi): one-time weight preparation for 3xTF32."""
     _cuda(w)
     w = w.contiguous()
-    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    both = torch.empty((2,) + tuple(w.shape), dtype=w.dtype, device=w.device)   # hi and lo adjacent: one 3-D TMA box fetches both
+    hi, lo = both[0], both[1]
     _lib.check(_lib.lib().rstnet_tf32_split_f32(w.data_ptr(), hi.data_ptr(), lo.data_ptr(), w.numel(), _stream()), "tf32_split")
     return hi, lo
 
