@@ -501,10 +501,11 @@ class _Plan:
             self.add(lambda: ops.gemm_rows(A.t, A.off(a_row0), A.bs, stride * Cin, pack["Wt"], out.t, out.off(out_row0),
                                            out.bs, N, B, T_out, **kw))
             return
-        if ffma:
+        if ffma and (Cin % 32 != 0 or (taps * (Cin // 32)) % 4 != 0 or self.precision != 0):
             # time-major layout on the CUDA cores: rows of a "batch" = the B streams of one output time step, taps are
-            # B*Cin apart.  Measured faster than the tensor-core kernel for the small-K resblock convs (launch lists
-            # profiles/r1_*): those are HBM / latency bound and the 3xTF32 pipeline's per-tile cost dominates.
+            # B*Cin apart.  Used for the resblock convs whose K loop is shorter than one 4-stage chunk of the
+            # persistent tensor-core kernel (1x1 convs with <= 64 input channels, k=3 convs with 64): those are
+            # HBM / latency bound and the 3xTF32 pipeline's per-tile cost dominates (launch lists profiles/r1_*).
             assert not tr_stride and out2 is None
             kw = dict(bias=pack["bias"], pre_act=pre, post_act=post, taps=taps, tap_stride=B * Cin)
             if R is not None:

@@ -32,6 +32,13 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
+// four lanes of one activation with the selector tested once (keeps rolled epilogue loops small)
+__device__ __forceinline__ float4 apply_act4(float4 v, int act) {
+  if (act == ACT_ELU) return make_float4(elu_f(v.x), elu_f(v.y), elu_f(v.z), elu_f(v.w));
+  if (act == ACT_GELU) return make_float4(gelu_f(v.x), gelu_f(v.y), gelu_f(v.z), gelu_f(v.w));
+  return v;
+}
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
   uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(src_bytes));

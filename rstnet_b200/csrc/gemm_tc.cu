@@ -341,6 +341,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int nchunks = total_k / CH;
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int tr_ti = my_tiles > 3 ? 3 : 0;   // the traced tile: steady state when the CTA has several
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -385,7 +386,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int t = blockIdx.x + ti * gridDim.x;
       const int nt = t % p.n_tiles, mt = t / p.n_tiles;
       n0 = nt * BN; ci = (mt % p.i_tiles) * TC_BM; co = (mt / p.i_tiles) * p.o_mul; kc = 0;
-      first_tile = ti == 0;
+      first_tile = ti == tr_ti;
       for (kit = 0; kit < total_k; kit += 4) {
         switch (v) {
           case 0: chunk(std::integral_constant<int, 0>{}); break;
@@ -433,7 +434,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     };
     int v = 0;
     for (int ti = 0; ti < my_tiles; ++ti) {
-      first_tile = ti == 0;
+      first_tile = ti == tr_ti;
       for (kit = 0; kit < total_k; kit += 4, ++cc) {
         switch (v) {
           case 0: chunk(std::integral_constant<int, 0>{}); break;
@@ -459,7 +460,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int g = grp; g < my_total; g += 2) {
         const int s = g % S, sa = g % TS_NA;
         mbar_wait(&full[s], (g / S) & 1);
-        if (tr && q == 0 && lane == 0 && g < total_k) p.trace[g * 8 + 1] = clock64();
+        if (tr && q == 0 && lane == 0 && g >= tr_ti * total_k && g < (tr_ti + 1) * total_k) p.trace[(g - tr_ti * total_k) * 8 + 1] = clock64();
         mbar_wait(&a_free[sa], ((g / TS_NA) & 1) ^ 1);
         tc_fence_after();
         const uint32_t base = smem0 + (uint32_t)(s * Cfg::STAGE_BYTES) + rowoff;
@@ -485,7 +486,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&a_ready[sa]);
-        if (tr && q == 0 && lane == 0 && g < total_k) p.trace[g * 8 + 2] = clock64();
+        if (tr && q == 0 && lane == 0 && g >= tr_ti * total_k && g < (tr_ti + 1) * total_k) p.trace[(g - tr_ti * total_k) * 8 + 2] = clock64();
       }
     };
     if (p.pre_act != ACT_NONE) run(std::true_type{}); else run(std::false_type{});
@@ -506,7 +507,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int buf = cc & 1;
         mbar_wait(&acc_full[buf], (cc >> 1) & 1);
         tc_fence_after();
-        if (tr && ti == 0 && threadIdx.x == 320) p.trace[chunk * 8 + 5] = clock64();
+        if (tr && ti == tr_ti && threadIdx.x == 320) p.trace[chunk * 8 + 5] = clock64();
 #pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 16) {
           uint32_t r[16], r2[16];
@@ -519,9 +520,12 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         tc_fence_before();
         mbar_arrive(&acc_empty[buf]);
-        if (tr && ti == 0 && threadIdx.x == 320) p.trace[chunk * 8 + 6] = clock64();
+        if (tr && ti == tr_ti && threadIdx.x == 320) p.trace[chunk * 8 + 6] = clock64();
       }
+      const bool etr = tr && ti == tr_ti && threadIdx.x == 320;
+      if (etr) p.trace[1 * 8 + 7] = clock64();
       named_bar_sync(1, 128);   // bias/scale of this tile are in smem (written before the chunk loop)
+      if (etr) p.trace[2 * 8 + 7] = clock64();
       // transpose through shared memory: thread = row while draining TMEM, 8 lanes = one 128-byte row segment when
       // storing, so every global access is a full line
       constexpr int LD = Cfg::OUT_LD;
@@ -531,10 +535,13 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int g4 = 0; g4 < BN / 4; ++g4)
         *reinterpret_cast<float4*>(stg + lane * LD + 4 * g4) = make_float4(acc[4 * g4], acc[4 * g4 + 1], acc[4 * g4 + 2], acc[4 * g4 + 3]);
       __syncwarp();
+      if (etr) p.trace[3 * 8 + 7] = clock64();
       const int cg = lane & 7, rsub = lane >> 3;
       const long long c_base = (long long)ot * p.c_o_stride, r_base = (long long)ot * p.r_o_stride;
       const int irow0 = i0 + q * 32 + rsub;
-#pragma unroll
+      // The store loop stays rolled: the activations are long inline sequences and an unrolled epilogue (thousands of
+      // instructions) thrashed the instruction cache -- it cost more than the tile's MMAs.
+#pragma unroll 1
       for (int pass = 0; pass < BN / 32; ++pass) {
         const int nl = pass * 32 + cg * 4, n = n0 + nl;
         if (n < p.N) {
@@ -546,33 +553,43 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             coff = (long long)j * p.c_split_stride + co;
             roff = (long long)j * p.r_split_stride + co;
           }
-          float4 rr[8];
-          if (p.R) {
+          float* srow = stg + rsub * LD + nl;
+          if (p.R) {   // (acc + bias) * scale + residual, residual rows fetched as one batch of eight loads
+            float4 rr[8];
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               const int i = irow0 + 4 * it;
               rr[it] = i < p.I_out ? __ldg(reinterpret_cast<const float4*>(p.R + r_base + (long long)i * p.r_i_stride + roff)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-          }
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int i = irow0 + 4 * it;
-            if (i < p.I_out) {
-              float4 v = *reinterpret_cast<const float4*>(stg + (rsub + 4 * it) * LD + nl);
+            for (int it = 0; it < 8; ++it) {
+              float4 v = *reinterpret_cast<const float4*>(srow + 4 * it * LD);
+              v.x = (v.x + bb.x) * ss.x + rr[it].x; v.y = (v.y + bb.y) * ss.y + rr[it].y;
+              v.z = (v.z + bb.z) * ss.z + rr[it].z; v.w = (v.w + bb.w) * ss.w + rr[it].w;
+              *reinterpret_cast<float4*>(srow + 4 * it * LD) = v;
+            }
+          } else {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              float4 v = *reinterpret_cast<const float4*>(srow + 4 * it * LD);
               v.x = (v.x + bb.x) * ss.x; v.y = (v.y + bb.y) * ss.y; v.z = (v.z + bb.z) * ss.z; v.w = (v.w + bb.w) * ss.w;
-              if (p.R) { v.x += rr[it].x; v.y += rr[it].y; v.z += rr[it].z; v.w += rr[it].w; }
-              const long long off = c_base + (long long)i * p.c_i_stride + coff;
-              if (p.C2)
-                *reinterpret_cast<float4*>(p.C2 + off) = make_float4(apply_act(v.x, p.act2), apply_act(v.y, p.act2), apply_act(v.z, p.act2), apply_act(v.w, p.act2));
-              if (p.post_act != ACT_NONE) {
-                v.x = apply_act(v.x, p.post_act); v.y = apply_act(v.y, p.post_act);
-                v.z = apply_act(v.z, p.post_act); v.w = apply_act(v.w, p.post_act);
-              }
-              *reinterpret_cast<float4*>(p.C + off) = v;
+              *reinterpret_cast<float4*>(srow + 4 * it * LD) = v;
             }
           }
+          if (etr) p.trace[(4 + 2 * pass) * 8 + 7] = clock64();
+          long long off = c_base + (long long)irow0 * p.c_i_stride + coff;
+#pragma unroll 1
+          for (int it = 0; it < 8; ++it, off += 4 * p.c_i_stride) {
+            if (irow0 + 4 * it < p.I_out) {
+              const float4 v = *reinterpret_cast<const float4*>(srow + 4 * it * LD);
+              if (p.C2) *reinterpret_cast<float4*>(p.C2 + off) = apply_act4(v, p.act2);
+              *reinterpret_cast<float4*>(p.C + off) = apply_act4(v, p.post_act);
+            }
+          }
+          if (etr) p.trace[(5 + 2 * pass) * 8 + 7] = clock64();
         }
       }
+      if (tr && ti == tr_ti && threadIdx.x == 320) p.trace[7] = clock64();
     }
   }
   if (timed) p.cta_times[blockIdx.x * 4 + 2] = gtime();
@@ -655,7 +672,12 @@ extern "C" int rstnet_tc_gemm_create(const rstnet_tc_gemm_desc* d, rstnet_tc_pla
   pl->bn = N >= 64 ? 64 : 32;
   // narrow the tile when the grid would leave most of the 148 SMs idle
   const int i_tiles = ceil_div(d->I_out, TC_BM);
-  while (pl->bn > 32 && (long long)i_tiles * d->O_out * ceil_div(N, pl->bn) < 148) pl->bn /= 2;
+  {
+    // persistent CTAs: rounds x per-tile cost (a BN=64 tile costs ~1.5x a BN=32 tile: same A transform, twice the MMAs)
+    const long long mt = (long long)i_tiles * d->O_out;
+    const long long t64 = mt * ceil_div(N, 64), t32 = mt * ceil_div(N, 32);
+    if (pl->bn == 64 && ((t32 + 147) / 148) * 2 <= ((t64 + 147) / 148) * 3) pl->bn = 32;
+  }
   pl->prec = d->precision;
   {
     cuuint64_t gdim[3] = {(cuuint64_t)d->a_c_extent, (cuuint64_t)d->a_i_extent, (cuuint64_t)d->a_o_extent};

@@ -34,7 +34,8 @@ print(f"CTA lifetime ns: mean {life.mean():.0f} min {life.min():.0f} max {life.m
       f"main {(c[:,2]-c[:,1]).float().mean():.0f} ns; all CTAs span {int(c[:,3].max()) - g0} ns")
 order = torch.argsort(c[:, 0])
 print("first CTA starts (ns):", [int(c[i, 0]) - g0 for i in order[:4]], " 149th..:", "")
+print("epilogue stamps (end, pre-bar, post-bar, staged, p0 phase1 done, p0 stored, p1 phase1, p1 stored):", [int(t[k,7]) - t0 for k in range(8)])
 print("kit  prod  landed  xformed  mma_start mma_issued | drain_b drain_e")
-for k in range(min(nk, 10)):
+for k in range(min(nk, 16)):
     r = [int(v) - t0 if int(v) else -1 for v in t[k]]
     print(f"{k:3d} {r[0]:6d} {r[1]:7d} {r[2]:8d} {r[3]:9d} {r[4]:9d} | {r[5]:7d} {r[6]:7d}")
