@@ -159,6 +159,8 @@ class MimiCodec(nn.Module):
         # precision of PyTorch's own cuDNN convolutions on GPUs): +8 % frames/s, waveform error 1.3e-3 of a 0.57 peak.
         self.tc_precision = 0
         self.decoder_precision = 0
+        # resblock convs (k=3 C->C/2, 1x1 C/2->C) on the tensor cores too; False keeps them on the CUDA-core kernel
+        self.resblock_tensor_cores = True
 
     # ------------------------------------------------------------------ parameters
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
@@ -501,11 +503,10 @@ class _Plan:
             self.add(lambda: ops.gemm_rows(A.t, A.off(a_row0), A.bs, stride * Cin, pack["Wt"], out.t, out.off(out_row0),
                                            out.bs, N, B, T_out, **kw))
             return
-        if ffma and (Cin % 32 != 0 or (taps * (Cin // 32)) % 4 != 0 or self.precision != 0):
+        if ffma and (Cin % 32 != 0 or self.precision != 0 or not self.eng.m.resblock_tensor_cores):
             # time-major layout on the CUDA cores: rows of a "batch" = the B streams of one output time step, taps are
-            # B*Cin apart.  Used for the resblock convs whose K loop is shorter than one 4-stage chunk of the
-            # persistent tensor-core kernel (1x1 convs with <= 64 input channels, k=3 convs with 64): those are
-            # HBM / latency bound and the 3xTF32 pipeline's per-tile cost dominates (launch lists profiles/r1_*).
+            # B*Cin apart.  Fallback for the resblock convs (single-pass TF32 decoder option, or
+            # resblock_tensor_cores = False to compare against the CUDA-core path).
             assert not tr_stride and out2 is None
             kw = dict(bias=pack["bias"], pre_act=pre, post_act=post, taps=taps, tap_stride=B * Cin)
             if R is not None:

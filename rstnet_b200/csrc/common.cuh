@@ -32,6 +32,22 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
+// Tensor-core epilogues: ELU through ex2.approx (|abs error| ~2e-7, below the 3xTF32 product error of the GEMM that
+// feeds it); the CUDA-core kernels keep expf.  The full-precision version cost more than the tile's MMAs.
+__device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
+template <int ACTC>
+__device__ __forceinline__ float4 apply_act4_tc(float4 v) {
+  if (ACTC == ACT_ELU) return make_float4(elu_fast(v.x), elu_fast(v.y), elu_fast(v.z), elu_fast(v.w));
+  if (ACTC == ACT_GELU) return make_float4(gelu_f(v.x), gelu_f(v.y), gelu_f(v.z), gelu_f(v.w));
+  return v;
+}
+
+__device__ __forceinline__ float4 apply_act4_tc(float4 v, int act) {
+  if (act == ACT_ELU) return apply_act4_tc<ACT_ELU>(v);
+  if (act == ACT_GELU) return apply_act4_tc<ACT_GELU>(v);
+  return v;
+}
+
 // four lanes of one activation with the selector tested once (keeps rolled epilogue loops small)
 __device__ __forceinline__ float4 apply_act4(float4 v, int act) {
   if (act == ACT_ELU) return make_float4(elu_f(v.x), elu_f(v.y), elu_f(v.z), elu_f(v.w));

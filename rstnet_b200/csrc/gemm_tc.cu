@@ -46,6 +46,7 @@ struct TcParams {
   int I_out, O_out, N, Kc;
   int taps, tap_di, tap_do, o_mul, kchunks;
   int pre_act, post_act, i_tiles;
+  int tma_store, c_tr;   // .ts kernel: epilogue through TMA tile stores (no residual); c_tr = output rows per o for n_split
   int m_tiles, n_tiles;  // (I tiles x O_out) and N tiles: the persistent .ts kernel walks m_tiles * n_tiles
   long long* trace;  // optional [total_k][8] clock64 stamps of CTA 0 (debug / profiling)
   long long* cta_times;  // optional [grid.x][4] %globaltimer: entry, setup done, mainloop+epilogue done, exit (blockIdx.y == 0)
@@ -303,13 +304,15 @@ struct TsCfg {
   static constexpr int STAGES = BN == 64 ? 5 : 6;
   static constexpr int OUT_LD = BN + 4;                       // padded row of the epilogue staging tile (floats)
   static constexpr int OUT_BYTES = 4 * 32 * OUT_LD * 4;       // one 32-row slab per drain warp
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/ + 4 * BN * 4 /*bias+scale x2*/ + OUT_BYTES;
+  static constexpr int CTRL_BYTES = 2048;                     // barriers (512) + bias/scale x2 (<= 1024), keeps the staging area 1024-aligned
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + CTRL_BYTES + OUT_BYTES;
   static constexpr int ACC_COLS = 2 * TC_NACC * BN;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW3, const TcParams p) {
+gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW3,
+                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const TcParams p) {
   using Cfg = TsCfg<BN>;
   constexpr int S = Cfg::STAGES;
   constexpr int CH = TC_CHUNK_STAGES;
@@ -330,15 +333,18 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* acc_empty = acc_full + 2;            // [2] (128 arrivals)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* sbs = reinterpret_cast<float*>(smem + S * Cfg::STAGE_BYTES + 512);  // [2][2*BN] bias | scale of the drain's tile
-  float* out_stage = sbs + 4 * BN;                                            // [4 warps][32][OUT_LD] epilogue transpose
+  float* out_stage = reinterpret_cast<float*>(smem + S * Cfg::STAGE_BYTES + Cfg::CTRL_BYTES);   // epilogue staging (1024-aligned)
 
   auto gtime = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (long long)t; };
   const bool timed = p.cta_times && threadIdx.x == 0;
   const bool tr = p.trace && blockIdx.x == 0;
   if (timed) p.cta_times[blockIdx.x * 4 + 0] = gtime();
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int total_k = p.taps * p.kchunks;   // multiple of 4 (host-checked)
-  const int nchunks = total_k / CH;
+  // A tile's K loop is padded to whole 4-stage chunks: the padding stages run the full barrier protocol (so the
+  // static slot / parity schedule holds) but move no data and issue no MMA.
+  const int total_k = p.taps * p.kchunks;
+  const int kpad = (total_k + CH - 1) / CH * CH;
+  const int nchunks = kpad / CH;
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int tr_ti = my_tiles > 3 ? 3 : 0;   // the traced tile: steady state when the CTA has several
@@ -346,6 +352,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW3);
+    if (p.tma_store) { tma_prefetch_desc(&tmC); if (p.C2) tma_prefetch_desc(&tmC2); }
     for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < TS_NA; ++s) { mbar_init(&a_ready[s], 128); mbar_init(&a_free[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
@@ -371,6 +378,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int s = (4 * V + u) % S;
           const uint32_t par = (uint32_t)(((4 * V + u) / S) & 1);
           mbar_wait(&empty[s], par ^ 1);
+          if (kit + u >= total_k) { mbar_arrive(&full[s]); continue; }   // padding stage
           if (tr && first_tile) p.trace[(kit + u) * 8 + 0] = clock64();
           uint8_t* st = smem + s * Cfg::STAGE_BYTES;
           mbar_arrive_expect_tx(&full[s], TC_A_BYTES + 2 * Cfg::B_BYTES);
@@ -387,7 +395,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int nt = t % p.n_tiles, mt = t / p.n_tiles;
       n0 = nt * BN; ci = (mt % p.i_tiles) * TC_BM; co = (mt / p.i_tiles) * p.o_mul; kc = 0;
       first_tile = ti == tr_ti;
-      for (kit = 0; kit < total_k; kit += 4) {
+      for (kit = 0; kit < kpad; kit += 4) {
         switch (v) {
           case 0: chunk(std::integral_constant<int, 0>{}); break;
           case 1: chunk(std::integral_constant<int, 1 % NV>{}); break;
@@ -419,10 +427,12 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (tr && first_tile) p.trace[(kit + u) * 8 + 3] = clock64();
           const uint32_t ah = a_tmem0 + (uint32_t)(u * 64), al = ah + 32u;
           const uint64_t db = desc0 + (uint64_t)((s * Cfg::STAGE_BYTES + TC_A_BYTES) >> 4);
+          if (kit + u < total_k) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            mma_tf32_ts(d0, ah + (uint32_t)(8 * k), db + (uint64_t)(2 * k), idesc2, (u == 0 && k == 0) ? 0u : 1u);
-            mma_tf32_ts(d1, al + (uint32_t)(8 * k), db + (uint64_t)(2 * k), idesc1, 1u);
+            for (int k = 0; k < 4; ++k) {
+              mma_tf32_ts(d0, ah + (uint32_t)(8 * k), db + (uint64_t)(2 * k), idesc2, (u == 0 && k == 0) ? 0u : 1u);
+              mma_tf32_ts(d1, al + (uint32_t)(8 * k), db + (uint64_t)(2 * k), idesc1, 1u);
+            }
           }
           tc_commit(&empty[s]);
           tc_commit(&a_free[u]);
@@ -435,7 +445,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int v = 0;
     for (int ti = 0; ti < my_tiles; ++ti) {
       first_tile = ti == tr_ti;
-      for (kit = 0; kit < total_k; kit += 4, ++cc) {
+      for (kit = 0; kit < kpad; kit += 4, ++cc) {
         switch (v) {
           case 0: chunk(std::integral_constant<int, 0>{}); break;
           case 1: chunk(std::integral_constant<int, 1 % NV>{}); break;
@@ -454,13 +464,20 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t rowoff = (uint32_t)(row * 128 + ((row & 7) << 4));   // chunk j of the swizzled row: rowoff ^ (j << 4)
     const uint32_t smem0 = smem_u32(smem);
     const uint32_t ta0 = a_tmem0 + ((uint32_t)(q * 32) << 16);
-    const int my_total = my_tiles * total_k;
+    const int my_total = my_tiles * kpad;
     auto run = [&](auto act_tag) {
       constexpr bool ACT = decltype(act_tag)::value;
-      for (int g = grp; g < my_total; g += 2) {
+      int kit = grp;   // stage index inside the tile (kpad is even, so a group keeps its parity across tiles)
+      for (int g = grp; g < my_total; g += 2, kit += 2) {
+        if (kit >= kpad) kit -= kpad;
         const int s = g % S, sa = g % TS_NA;
         mbar_wait(&full[s], (g / S) & 1);
-        if (tr && q == 0 && lane == 0 && g >= tr_ti * total_k && g < (tr_ti + 1) * total_k) p.trace[(g - tr_ti * total_k) * 8 + 1] = clock64();
+        if (kit >= total_k) {   // padding stage: nothing to convert
+          mbar_wait(&a_free[sa], ((g / TS_NA) & 1) ^ 1);
+          mbar_arrive(&a_ready[sa]);
+          continue;
+        }
+        if (tr && q == 0 && lane == 0 && g >= tr_ti * kpad && g < (tr_ti + 1) * kpad) p.trace[(g - tr_ti * kpad) * 8 + 1] = clock64();
         mbar_wait(&a_free[sa], ((g / TS_NA) & 1) ^ 1);
         tc_fence_after();
         const uint32_t base = smem0 + (uint32_t)(s * Cfg::STAGE_BYTES) + rowoff;
@@ -486,12 +503,13 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&a_ready[sa]);
-        if (tr && q == 0 && lane == 0 && g >= tr_ti * total_k && g < (tr_ti + 1) * total_k) p.trace[(g - tr_ti * total_k) * 8 + 2] = clock64();
+        if (tr && q == 0 && lane == 0 && g >= tr_ti * kpad && g < (tr_ti + 1) * kpad) p.trace[(g - tr_ti * kpad) * 8 + 2] = clock64();
       }
     };
     if (p.pre_act != ACT_NONE) run(std::true_type{}); else run(std::false_type{});
   } else {
     const int q = warp % 4, dt = threadIdx.x - 320;
+    const int row = q * 32 + lane;
     int cc = 0;
     for (int ti = 0; ti < my_tiles; ++ti) {
       const int t = blockIdx.x + ti * gridDim.x;
@@ -526,6 +544,54 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (etr) p.trace[1 * 8 + 7] = clock64();
       named_bar_sync(1, 128);   // bias/scale of this tile are in smem (written before the chunk loop)
       if (etr) p.trace[2 * 8 + 7] = clock64();
+      if (p.tma_store) {
+        // Epilogue without per-thread global stores: the row (thread = TMEM lane) is finished in registers, written
+        // into 128-byte-swizzled [128 x 32] boxes in shared memory and one thread issues TMA tile stores.  Two
+        // outputs (raw + ELU'd copy for the next layer) reuse the boxes after the first store has been read out.
+        uint8_t* boxes = reinterpret_cast<uint8_t*>(out_stage);   // [BN/32][128 rows][128 B], 1024-aligned
+        const uint32_t rsw = (uint32_t)(row * 128), rx = (uint32_t)(row & 7);
+        const int nout = p.C2 ? 2 : 1;
+        for (int oi = 0; oi < nout; ++oi) {
+          const bool second = (nout == 2) && oi == 0;   // C2 first, C last
+          const int act = second ? p.act2 : p.post_act;
+          if (dt == 0) bulk_wait_read0();               // earlier stores of this CTA no longer read the boxes
+          named_bar_sync(2, 128);
+          auto stage_rows = [&](auto act_c) {   // one instantiation per activation: only the executed one is fetched
+            constexpr int ACTC = decltype(act_c)::value;
+#pragma unroll
+            for (int g8 = 0; g8 < BN / 32; ++g8) {
+              uint8_t* bx = boxes + g8 * (TC_BM * 128) + rsw;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int c = g8 * 32 + 4 * j;
+                const float4 bb = *reinterpret_cast<const float4*>(sb + c);
+                const float4 ss = *reinterpret_cast<const float4*>(sb + BN + c);
+                const float4 v = make_float4((acc[c] + bb.x) * ss.x, (acc[c + 1] + bb.y) * ss.y, (acc[c + 2] + bb.z) * ss.z, (acc[c + 3] + bb.w) * ss.w);
+                *reinterpret_cast<float4*>(bx + (((uint32_t)j ^ rx) << 4)) = apply_act4_tc<ACTC>(v);
+              }
+            }
+          };
+          if (act == ACT_ELU) stage_rows(std::integral_constant<int, ACT_ELU>{});
+          else if (act == ACT_GELU) stage_rows(std::integral_constant<int, ACT_GELU>{});
+          else stage_rows(std::integral_constant<int, ACT_NONE>{});
+          fence_proxy_async_smem();
+          named_bar_sync(3, 128);
+          if (dt == 0) {
+            const CUtensorMap* tm = second ? &tmC2 : &tmC;
+            for (int g8 = 0; g8 < BN / 32; ++g8) {
+              const int n = n0 + g8 * 32;
+              if (n < p.N) {
+                int c0 = n, c2 = ot;
+                if (p.n_split > 0) { c0 = n % p.n_split; c2 = ot * p.c_tr + n / p.n_split; }
+                tma_store_3d(tm, boxes + g8 * (TC_BM * 128), c0, i0, c2);
+              }
+            }
+            bulk_commit();
+          }
+        }
+        if (tr && ti == tr_ti && threadIdx.x == 320) p.trace[7] = clock64();
+        continue;
+      }
       // transpose through shared memory: thread = row while draining TMEM, 8 lanes = one 128-byte row segment when
       // storing, so every global access is a full line
       constexpr int LD = Cfg::OUT_LD;
@@ -582,8 +648,8 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int it = 0; it < 8; ++it, off += 4 * p.c_i_stride) {
             if (irow0 + 4 * it < p.I_out) {
               const float4 v = *reinterpret_cast<const float4*>(srow + 4 * it * LD);
-              if (p.C2) *reinterpret_cast<float4*>(p.C2 + off) = apply_act4(v, p.act2);
-              *reinterpret_cast<float4*>(p.C + off) = apply_act4(v, p.post_act);
+              if (p.C2) *reinterpret_cast<float4*>(p.C2 + off) = apply_act4_tc(v, p.act2);
+              *reinterpret_cast<float4*>(p.C + off) = apply_act4_tc(v, p.post_act);
             }
           }
           if (etr) p.trace[(5 + 2 * pass) * 8 + 7] = clock64();
@@ -592,6 +658,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (tr && ti == tr_ti && threadIdx.x == 320) p.trace[7] = clock64();
     }
   }
+  if (threadIdx.x == 320) bulk_wait0();   // the issuing thread's TMA stores are complete before the CTA (and its smem) goes away
   if (timed) p.cta_times[blockIdx.x * 4 + 2] = gtime();
   tc_fence_before();
   __syncthreads();
@@ -619,6 +686,7 @@ using namespace rstnet;
 
 struct rstnet_tc_plan {
   CUtensorMap tmA, tmW, tmWlo;
+  CUtensorMap tmC, tmC2;  // output tiles of the .ts kernel's TMA-store epilogue
   CUtensorMap tmW3;  // [2 (hi, lo)][N][K] when W_lo follows W at a 16-byte-aligned distance (.ts kernel)
   bool ts_ok;
   TcParams p;
@@ -635,7 +703,7 @@ static int tc_launch_ts(const rstnet_tc_plan* pl, cudaStream_t st) {
     cudaFuncSetAttribute(gemm_tc_ts_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     attr = true;
   }
-  gemm_tc_ts_kernel<BN><<<pl->grid_ts, TC_THREADS, Cfg::SMEM_BYTES, st>>>(pl->tmA, pl->tmW3, pl->p);
+  gemm_tc_ts_kernel<BN><<<pl->grid_ts, TC_THREADS, Cfg::SMEM_BYTES, st>>>(pl->tmA, pl->tmW3, pl->tmC, pl->tmC2, pl->p);
   count_launch();
   return check_launch("gemm_tc_ts");
 }
@@ -709,10 +777,10 @@ extern "C" int rstnet_tc_gemm_create(const rstnet_tc_gemm_desc* d, rstnet_tc_pla
       set_error("tc_gemm_create: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
       return 3;
     }
-    // persistent .ts kernel: 3xTF32 with whole 4-stage chunks and hi/lo weights reachable through one descriptor
+    // persistent .ts kernel: 3xTF32 with hi/lo weights reachable through one descriptor
     pl->ts_ok = false;
     const long long wdiff = d->W_lo ? (const char*)d->W_lo - (const char*)d->W : 0;
-    if (pl->prec == 0 && wdiff > 0 && wdiff % 16 == 0 && (d->taps * (d->Kc / TC_BKE)) % TC_CHUNK_STAGES == 0) {
+    if (pl->prec == 0 && wdiff > 0 && wdiff % 16 == 0) {
       cuuint64_t gdim3[3] = {(cuuint64_t)d->taps * d->Kc, (cuuint64_t)N, 2};
       cuuint64_t gstr3[2] = {(cuuint64_t)d->taps * d->Kc * 4, (cuuint64_t)wdiff};
       cuuint32_t box3[3] = {TC_BKE, (cuuint32_t)pl->bn, 2};
@@ -720,6 +788,25 @@ extern "C" int rstnet_tc_gemm_create(const rstnet_tc_gemm_desc* d, rstnet_tc_pla
       r = enc(&pl->tmW3, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)d->W, gdim3, gstr3, box3, estr3, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       pl->ts_ok = r == CUDA_SUCCESS;
+    }
+    // TMA-store epilogue: no residual, 32-column boxes, 16-byte aligned rows
+    pl->p.tma_store = 0; pl->p.c_tr = 1;
+    const bool split = d->n_split > 0;
+    if (pl->ts_ok && !d->R && N % 32 == 0 && (!split || (d->n_split % 32 == 0 && d->c_split_stride > 0 && d->c_o_stride % d->c_split_stride == 0)) &&
+        d->c_i_stride % 4 == 0 && d->c_o_stride % 4 == 0 && ((uintptr_t)d->C % 16) == 0 && (!d->C2 || ((uintptr_t)d->C2 % 16) == 0)) {
+      const long long tr_rows = split ? d->c_o_stride / d->c_split_stride : 1;
+      cuuint64_t cdim[3] = {(cuuint64_t)(split ? d->n_split : N), (cuuint64_t)d->I_out, (cuuint64_t)(d->O_out * tr_rows)};
+      cuuint64_t cstr[2] = {(cuuint64_t)d->c_i_stride * 4, (cuuint64_t)(split ? d->c_split_stride : (d->O_out > 1 ? d->c_o_stride : d->c_i_stride * d->I_out)) * 4};
+      cuuint32_t cbox[3] = {32, TC_BM, 1};
+      cuuint32_t cest[3] = {1, 1, 1};
+      CUresult rc = enc(&pl->tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)d->C, cdim, cstr, cbox, cest, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (rc == CUDA_SUCCESS && d->C2)
+        rc = enc(&pl->tmC2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)d->C2, cdim, cstr, cbox, cest, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      else if (rc == CUDA_SUCCESS)
+        pl->tmC2 = pl->tmC;
+      if (rc == CUDA_SUCCESS) { pl->p.tma_store = 1; pl->p.c_tr = (int)tr_rows; }
     }
   }
   TcParams& p = pl->p;

@@ -261,25 +261,86 @@ __device__ __forceinline__ uint32_t hash_u32(uint32_t a, uint32_t b, uint32_t c,
 // logits [rows][V] bf16, candidates restricted to ids < n_valid.  top_k <= 0: argmax (first maximum).
 // top_k > 0: the top_k largest logits, weights exp((l - max)/temp), token = argmax_i w_i / Exp(1)_i
 // (= torch's exponential-noise multinomial over the top-k probabilities, sampling.py:43-46, 57-59).
+//
+// Large vocabularies (the 152k text head) first shrink the row to a candidate list: bf16 has 16 key bits, so two
+// 256-bin histogram passes give the exact key of the top_k-th largest logit; every logit with key >= that threshold
+// (top_k of them plus ties) is compacted into shared memory and the ordered selection below runs on the list instead
+// of re-scanning the row top_k times.  Same result as the full scan: (value desc, index asc) order.
+constexpr int SAMPLE_CAND = 1024;
+constexpr int SAMPLE_HISTS = 16;
+
+__device__ __forceinline__ uint32_t bf16_order_key(bf16 v) {
+  const uint32_t u = (uint32_t)__bfloat16_as_ushort(v);
+  return (u & 0x8000u) ? (~u & 0xFFFFu) : (u | 0x8000u);
+}
+
 __global__ void sample_kernel(const bf16* __restrict__ logits, int V, int n_valid, int top_k, float temp, uint32_t seed,
                               const long long* __restrict__ step_counter, long long* __restrict__ tokens, int tok_stride) {
   __shared__ float s_val[32];
   __shared__ int s_idx[32];
   __shared__ float top_v[64];
   __shared__ int top_i[64];
+  __shared__ int hist[SAMPLE_HISTS][256];
+  __shared__ float cand_v[SAMPLE_CAND];
+  __shared__ int cand_i[SAMPLE_CAND];
+  __shared__ int s_sel[4];   // [0] high-byte bin, [1] count above it, [2] threshold key, [3] candidate count
   const int row = blockIdx.x;
   const bf16* lr = logits + (long long)row * V;
   const int kk = top_k <= 0 ? 1 : (top_k > 64 ? 64 : top_k);
+  const int tid = threadIdx.x, nthr = blockDim.x;
+
+  int n_items = n_valid;
+  bool from_list = false;
+  if (kk > 1 && n_valid > 4 * SAMPLE_CAND) {
+    int* myh = hist[(tid / 32) % SAMPLE_HISTS];
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int i = tid; i < SAMPLE_HISTS * 256; i += nthr) (&hist[0][0])[i] = 0;
+      __syncthreads();
+      const int b1 = pass ? s_sel[0] : 0;
+      for (int i = tid; i < n_valid; i += nthr) {
+        const uint32_t k = bf16_order_key(lr[i]);
+        if (pass == 0) atomicAdd(&myh[k >> 8], 1);
+        else if ((int)(k >> 8) == b1) atomicAdd(&myh[k & 255u], 1);
+      }
+      __syncthreads();
+      if (tid < 256) {
+        int c = 0;
+#pragma unroll
+        for (int h = 0; h < SAMPLE_HISTS; ++h) c += hist[h][tid];
+        hist[0][tid] = c;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int above = pass ? s_sel[1] : 0, b = 255;
+        while (b > 0 && above + hist[0][b] < kk) { above += hist[0][b]; --b; }
+        if (pass == 0) { s_sel[0] = b; s_sel[1] = above; }
+        else { s_sel[2] = (s_sel[0] << 8) | b; s_sel[3] = 0; }
+      }
+      __syncthreads();
+    }
+    const uint32_t thr = (uint32_t)s_sel[2];
+    for (int i = tid; i < n_valid; i += nthr) {
+      const bf16 v = lr[i];
+      if (bf16_order_key(v) >= thr) {
+        const int slot = atomicAdd(&s_sel[3], 1);
+        if (slot < SAMPLE_CAND) { cand_v[slot] = b2f(v); cand_i[slot] = i; }
+      }
+    }
+    __syncthreads();
+    if (s_sel[3] <= SAMPLE_CAND) { from_list = true; n_items = s_sel[3]; }   // else: massive ties, scan the row
+  }
+
   float last_v = INFINITY;
   int last_i = -1;
   for (int r = 0; r < kk; ++r) {
     // largest (value, lowest index) strictly after (last_v, last_i) in the order (value desc, index asc)
     float bv = -INFINITY;
     int bi = 0x7fffffff;
-    for (int i = threadIdx.x; i < n_valid; i += blockDim.x) {
-      const float v = b2f(lr[i]);
-      const bool after = v < last_v || (v == last_v && i > last_i);
-      if (after && (v > bv || (v == bv && i < bi))) { bv = v; bi = i; }
+    for (int i = tid; i < n_items; i += nthr) {
+      const float v = from_list ? cand_v[i] : b2f(lr[i]);
+      const int id = from_list ? cand_i[i] : i;
+      const bool after = v < last_v || (v == last_v && id > last_i);
+      if (after && (v > bv || (v == bv && id < bi))) { bv = v; bi = id; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -287,24 +348,24 @@ __global__ void sample_kernel(const bf16* __restrict__ logits, int V, int n_vali
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
       if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
     }
-    if (threadIdx.x % 32 == 0) { s_val[threadIdx.x / 32] = bv; s_idx[threadIdx.x / 32] = bi; }
+    if (tid % 32 == 0) { s_val[tid / 32] = bv; s_idx[tid / 32] = bi; }
     __syncthreads();
-    if (threadIdx.x < 32) {
-      bv = threadIdx.x < blockDim.x / 32 ? s_val[threadIdx.x] : -INFINITY;
-      bi = threadIdx.x < blockDim.x / 32 ? s_idx[threadIdx.x] : 0x7fffffff;
+    if (tid < 32) {
+      bv = tid < nthr / 32 ? s_val[tid] : -INFINITY;
+      bi = tid < nthr / 32 ? s_idx[tid] : 0x7fffffff;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
       }
-      if (threadIdx.x == 0) { top_v[r] = bv; top_i[r] = bi; }
+      if (tid == 0) { top_v[r] = bv; top_i[r] = bi; }
     }
     __syncthreads();
     last_v = top_v[r];
     last_i = top_i[r];
   }
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     int pick = top_i[0];
     if (top_k > 0) {
       const uint32_t stepc = step_counter ? (uint32_t)(*step_counter) : 0u;

@@ -18,7 +18,8 @@ def _rel(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp(min=1e-6)).item()
 
 
-@pytest.mark.parametrize("M,K,N", [(128, 32, 32), (256, 512, 512), (512, 2048, 512), (200, 512, 1536), (64, 64, 128), (300, 96, 36)])
+@pytest.mark.parametrize("M,K,N", [(128, 32, 32), (256, 512, 512), (512, 2048, 512), (200, 512, 1536), (64, 64, 128), (300, 96, 36),
+                                   (38400, 96, 64), (40000, 32, 64), (25000, 256, 128)])  # several tiles per persistent CTA, padded K loops
 @pytest.mark.parametrize("prec,tol", [(0, 2e-6), (1, 3e-3)])
 def test_tc_linear(M, K, N, prec, tol):
     g = torch.Generator().manual_seed(M + K + N)

@@ -134,6 +134,34 @@ def test_sampling_greedy_and_distribution():
     assert set(out.cpu().tolist()) <= {2, 4, 3}
 
 
+def test_sampling_large_vocab_candidate_list_matches_full_scan():
+    """The 152k-entry text head goes through the histogram-select candidate list; it must pick exactly what the plain
+    top_k-pass scan picks (same seed, same (value desc, index asc) order), ties at the threshold included."""
+    lib, st = _lib.lib(), ops._stream()
+    g = torch.Generator().manual_seed(11)
+    rows, V, small = 32, 151936, 4000
+    logits = (torch.randn(rows, V, generator=g) * 2.0).to(BF)
+    logits[:, small:] = torch.minimum(logits[:, small:], torch.tensor(1.0).to(BF))   # the whole top-k lives in ids < small
+    logits[:, :small] += 3.0
+    logits[3, 10:40] = 7.5      # 30 equal values straddling the top-25 boundary -> lowest ids win
+    logits[4, :] = 0.25         # massive tie: falls back to the full scan
+    ld = logits.to(DEV).contiguous()
+    a = torch.zeros(rows, dtype=torch.int64, device=DEV)
+    b = torch.zeros(rows, dtype=torch.int64, device=DEV)
+    for top_k, seed in ((25, 5), (64, 6), (2, 7)):
+        _lib.check(lib.rstnet_lm_sample_bf16(ld.data_ptr(), rows, V, small, top_k, 0.8, seed, None, a.data_ptr(), 1, st))
+        _lib.check(lib.rstnet_lm_sample_bf16(ld.data_ptr(), rows, V, V, top_k, 0.8, seed, None, b.data_ptr(), 1, st))
+        torch.cuda.synchronize()
+        keep = torch.ones(rows, dtype=torch.bool); keep[4] = False   # row 4's top-k is not inside ids < small
+        assert torch.equal(a.cpu()[keep], b.cpu()[keep]), top_k
+        topk = torch.topk(logits.float(), top_k, dim=-1).values[:, -1:]
+        picked = logits.float().gather(1, b.cpu()[:, None])
+        assert (picked >= topk).all()
+        assert int(b[4]) < top_k     # all-equal row: the top-k are ids 0..top_k-1
+    _lib.check(lib.rstnet_lm_sample_bf16(ld.data_ptr(), rows, V, V, 0, 1.0, 1, None, b.data_ptr(), 1, st))
+    assert torch.equal(b.cpu(), torch.argmax(logits.float(), -1))
+
+
 @pytest.fixture(scope="module")
 def small_lm():
     cfg = L.SMALL
