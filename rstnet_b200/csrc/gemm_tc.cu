@@ -312,7 +312,8 @@ struct TsCfg {
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW3,
-                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const TcParams p) {
+                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
+                  const __grid_constant__ CUtensorMap tmR, const TcParams p) {
   using Cfg = TsCfg<BN>;
   constexpr int S = Cfg::STAGES;
   constexpr int CH = TC_CHUNK_STAGES;
@@ -331,7 +332,8 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* a_free = bars + 2 * S + TS_NA;       // [NA] MMAs reading that TMEM stage retired
   uint64_t* acc_full = bars + 2 * S + 2 * TS_NA; // [2]
   uint64_t* acc_empty = acc_full + 2;            // [2] (128 arrivals)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* r_full = acc_empty + 2;              // residual tile landed in the epilogue boxes
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(r_full + 1);
   float* sbs = reinterpret_cast<float*>(smem + S * Cfg::STAGE_BYTES + 512);  // [2][2*BN] bias | scale of the drain's tile
   float* out_stage = reinterpret_cast<float*>(smem + S * Cfg::STAGE_BYTES + Cfg::CTRL_BYTES);   // epilogue staging (1024-aligned)
 
@@ -352,10 +354,11 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW3);
-    if (p.tma_store) { tma_prefetch_desc(&tmC); if (p.C2) tma_prefetch_desc(&tmC2); }
+    if (p.tma_store) { tma_prefetch_desc(&tmC); if (p.C2) tma_prefetch_desc(&tmC2); if (p.R) tma_prefetch_desc(&tmR); }
     for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < TS_NA; ++s) { mbar_init(&a_ready[s], 128); mbar_init(&a_free[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
+    mbar_init(r_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_ptr);
@@ -518,6 +521,22 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       float* sb = sbs + (ti & 1) * 2 * BN;
       if (dt < BN) sb[dt] = (p.bias && n0 + dt < p.N) ? p.bias[n0 + dt] : 0.f;
       else if (dt < 2 * BN) sb[dt] = (p.scale && n0 + dt - BN < p.N) ? p.scale[n0 + dt - BN] : 1.f;
+      if (p.tma_store && p.R && dt == 0) {
+        // residual tile -> epilogue boxes while the K loop runs (the boxes are free once the previous store was read out)
+        bulk_wait_read0();
+        uint8_t* boxes = reinterpret_cast<uint8_t*>(out_stage);
+        int nb = 0;
+        for (int g8 = 0; g8 < BN / 32; ++g8) nb += (n0 + g8 * 32 < p.N) ? 1 : 0;
+        mbar_arrive_expect_tx(r_full, (uint32_t)(nb * TC_BM * 128));
+        for (int g8 = 0; g8 < BN / 32; ++g8) {
+          const int n = n0 + g8 * 32;
+          if (n < p.N) {
+            int c0 = n, c2 = ot;
+            if (p.n_split > 0) { c0 = n % p.n_split; c2 = ot * p.c_tr + n / p.n_split; }
+            tma_load_3d(boxes + g8 * (TC_BM * 128), &tmR, r_full, c0, i0, c2);
+          }
+        }
+      }
       float acc[BN];
 #pragma unroll
       for (int j = 0; j < BN; ++j) acc[j] = 0.f;
@@ -554,10 +573,13 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int oi = 0; oi < nout; ++oi) {
           const bool second = (nout == 2) && oi == 0;   // C2 first, C last
           const int act = second ? p.act2 : p.post_act;
-          if (dt == 0) bulk_wait_read0();               // earlier stores of this CTA no longer read the boxes
-          named_bar_sync(2, 128);
-          auto stage_rows = [&](auto act_c) {   // one instantiation per activation: only the executed one is fetched
+          if (!p.R) {
+            if (dt == 0) bulk_wait_read0();             // earlier stores of this CTA no longer read the boxes
+            named_bar_sync(2, 128);
+          }
+          auto stage_rows = [&](auto act_c, auto res_c) {   // one instantiation per activation: only the executed one is fetched
             constexpr int ACTC = decltype(act_c)::value;
+            constexpr bool RES = decltype(res_c)::value;
 #pragma unroll
             for (int g8 = 0; g8 < BN / 32; ++g8) {
               uint8_t* bx = boxes + g8 * (TC_BM * 128) + rsw;
@@ -566,14 +588,20 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int c = g8 * 32 + 4 * j;
                 const float4 bb = *reinterpret_cast<const float4*>(sb + c);
                 const float4 ss = *reinterpret_cast<const float4*>(sb + BN + c);
-                const float4 v = make_float4((acc[c] + bb.x) * ss.x, (acc[c + 1] + bb.y) * ss.y, (acc[c + 2] + bb.z) * ss.z, (acc[c + 3] + bb.w) * ss.w);
-                *reinterpret_cast<float4*>(bx + (((uint32_t)j ^ rx) << 4)) = apply_act4_tc<ACTC>(v);
+                float4 v = make_float4((acc[c] + bb.x) * ss.x, (acc[c + 1] + bb.y) * ss.y, (acc[c + 2] + bb.z) * ss.z, (acc[c + 3] + bb.w) * ss.w);
+                float4* slot = reinterpret_cast<float4*>(bx + (((uint32_t)j ^ rx) << 4));
+                if (RES) { const float4 rr = *slot; v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
+                *slot = apply_act4_tc<ACTC>(v);
               }
             }
           };
-          if (act == ACT_ELU) stage_rows(std::integral_constant<int, ACT_ELU>{});
-          else if (act == ACT_GELU) stage_rows(std::integral_constant<int, ACT_GELU>{});
-          else stage_rows(std::integral_constant<int, ACT_NONE>{});
+          if (p.R) {
+            mbar_wait(r_full, (uint32_t)(ti & 1));   // one residual load per tile
+            if (act == ACT_ELU) stage_rows(std::integral_constant<int, ACT_ELU>{}, std::true_type{});
+            else stage_rows(std::integral_constant<int, ACT_NONE>{}, std::true_type{});
+          } else if (act == ACT_ELU) stage_rows(std::integral_constant<int, ACT_ELU>{}, std::false_type{});
+          else if (act == ACT_GELU) stage_rows(std::integral_constant<int, ACT_GELU>{}, std::false_type{});
+          else stage_rows(std::integral_constant<int, ACT_NONE>{}, std::false_type{});
           fence_proxy_async_smem();
           named_bar_sync(3, 128);
           if (dt == 0) {
@@ -686,7 +714,7 @@ using namespace rstnet;
 
 struct rstnet_tc_plan {
   CUtensorMap tmA, tmW, tmWlo;
-  CUtensorMap tmC, tmC2;  // output tiles of the .ts kernel's TMA-store epilogue
+  CUtensorMap tmC, tmC2, tmR;  // output (and residual) tiles of the .ts kernel's TMA-store epilogue
   CUtensorMap tmW3;  // [2 (hi, lo)][N][K] when W_lo follows W at a 16-byte-aligned distance (.ts kernel)
   bool ts_ok;
   TcParams p;
@@ -703,7 +731,7 @@ static int tc_launch_ts(const rstnet_tc_plan* pl, cudaStream_t st) {
     cudaFuncSetAttribute(gemm_tc_ts_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     attr = true;
   }
-  gemm_tc_ts_kernel<BN><<<pl->grid_ts, TC_THREADS, Cfg::SMEM_BYTES, st>>>(pl->tmA, pl->tmW3, pl->tmC, pl->tmC2, pl->p);
+  gemm_tc_ts_kernel<BN><<<pl->grid_ts, TC_THREADS, Cfg::SMEM_BYTES, st>>>(pl->tmA, pl->tmW3, pl->tmC, pl->tmC2, pl->tmR, pl->p);
   count_launch();
   return check_launch("gemm_tc_ts");
 }
@@ -791,8 +819,11 @@ extern "C" int rstnet_tc_gemm_create(const rstnet_tc_gemm_desc* d, rstnet_tc_pla
     }
     // TMA-store epilogue: no residual, 32-column boxes, 16-byte aligned rows
     pl->p.tma_store = 0; pl->p.c_tr = 1;
-    const bool split = d->n_split > 0;
-    if (pl->ts_ok && !d->R && N % 32 == 0 && (!split || (d->n_split % 32 == 0 && d->c_split_stride > 0 && d->c_o_stride % d->c_split_stride == 0)) &&
+    const bool split = d->n_split > 0, split0 = split;
+    const bool res_ok = !d->R || (!d->C2 && (d->post_act == ACT_NONE || d->post_act == ACT_ELU) && d->r_i_stride % 4 == 0 && d->r_o_stride % 4 == 0 &&
+                                  ((uintptr_t)d->R % 16) == 0 && (!split0 || (d->r_split_stride > 0 && d->r_o_stride % d->r_split_stride == 0 &&
+                                                                                  d->r_o_stride / d->r_split_stride == d->c_o_stride / (d->c_split_stride > 0 ? d->c_split_stride : 1))));
+    if (pl->ts_ok && res_ok && N % 32 == 0 && (!split || (d->n_split % 32 == 0 && d->c_split_stride > 0 && d->c_o_stride % d->c_split_stride == 0)) &&
         d->c_i_stride % 4 == 0 && d->c_o_stride % 4 == 0 && ((uintptr_t)d->C % 16) == 0 && (!d->C2 || ((uintptr_t)d->C2 % 16) == 0)) {
       const long long tr_rows = split ? d->c_o_stride / d->c_split_stride : 1;
       cuuint64_t cdim[3] = {(cuuint64_t)(split ? d->n_split : N), (cuuint64_t)d->I_out, (cuuint64_t)(d->O_out * tr_rows)};
@@ -806,6 +837,12 @@ extern "C" int rstnet_tc_gemm_create(const rstnet_tc_gemm_desc* d, rstnet_tc_pla
                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       else if (rc == CUDA_SUCCESS)
         pl->tmC2 = pl->tmC;
+      pl->tmR = pl->tmC;
+      if (rc == CUDA_SUCCESS && d->R) {
+        cuuint64_t rstr[2] = {(cuuint64_t)d->r_i_stride * 4, (cuuint64_t)(split ? d->r_split_stride : (d->O_out > 1 ? d->r_o_stride : d->r_i_stride * d->I_out)) * 4};
+        rc = enc(&pl->tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)d->R, cdim, rstr, cbox, cest, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      }
       if (rc == CUDA_SUCCESS) { pl->p.tma_store = 1; pl->p.c_tr = (int)tr_rows; }
     }
   }
