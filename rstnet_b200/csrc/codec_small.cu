@@ -32,7 +32,8 @@ __global__ void conv_cin1_kernel(const float* __restrict__ x, long long xbs, lon
       for (int j = 0; j < 16; ++j)
         if (j < k) acc = fmaf(xs[t + j], wr[j], acc);
       acc += bv;
-      if (out2) out2[(long long)b * obs + (t0 + t) * ots + co] = apply_act(acc, act2);
+      // out2 exists only for the tensor-core plans (pre-activated copy for the next conv): same ex2-based ELU as their epilogues
+      if (out2) out2[(long long)b * obs + (t0 + t) * ots + co] = act2 == ACT_ELU ? elu_fast(acc) : apply_act(acc, act2);
       out[(long long)b * obs + (t0 + t) * ots + co] = apply_act(acc, post_act);
     }
   }
@@ -56,9 +57,17 @@ __global__ void conv_cout1_kernel(const float* __restrict__ x, long long xbs, lo
   const int nrows = (int)min(32LL, (long long)T - t0) + k - 1;
   if (t0 < T) {
     const int total = nrows * Cin;
-    for (int i = lane; i < total; i += 32) {
-      int r = i / Cin, c = i % Cin;
-      xs[r * (Cin + 1) + c] = xb[(t0 + r) * xts + c];
+    if ((Cin & (Cin - 1)) == 0) {   // power-of-two channel count: shift / mask instead of a division per element
+      const int sh = 31 - __clz(Cin);
+      for (int i = lane; i < total; i += 32) {
+        const int r = i >> sh, c = i & (Cin - 1);
+        xs[r * (Cin + 1) + c] = xb[(t0 + r) * xts + c];
+      }
+    } else {
+      for (int i = lane; i < total; i += 32) {
+        int r = i / Cin, c = i % Cin;
+        xs[r * (Cin + 1) + c] = xb[(t0 + r) * xts + c];
+      }
     }
   }
   __syncthreads();
@@ -69,7 +78,15 @@ __global__ void conv_cout1_kernel(const float* __restrict__ x, long long xbs, lo
     for (int j = 0; j < k; ++j) {
       const float* xr = xs + (lane + j) * (Cin + 1);
       const float* wr = ws + j * Cin;
-      for (int c = 0; c < Cin; ++c) acc = fmaf(xr[c], wr[c], acc);
+      int c = 0;
+      if ((Cin & 3) == 0 && ((j * Cin) & 3) == 0) {
+        for (; c < Cin; c += 4) {   // weights as one broadcast 128-bit read per four taps; same accumulation order
+          const float4 w4 = *reinterpret_cast<const float4*>(wr + c);
+          acc = fmaf(xr[c], w4.x, acc); acc = fmaf(xr[c + 1], w4.y, acc);
+          acc = fmaf(xr[c + 2], w4.z, acc); acc = fmaf(xr[c + 3], w4.w, acc);
+        }
+      }
+      for (; c < Cin; ++c) acc = fmaf(xr[c], wr[c], acc);
     }
     out[(long long)b * obs + t] = acc + (bias ? bias[0] : 0.f);
   }

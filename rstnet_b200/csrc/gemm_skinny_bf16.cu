@@ -10,6 +10,8 @@
 // models/lit_model.py:399-403) and in the depth transformer (modules/transformer.py:155-179, gating.py:12-21).
 #include <cuda_bf16.h>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "../../include/rstnet_b200.h"
@@ -152,17 +154,26 @@ __global__ void skinny_finalize_kernel(const float* __restrict__ partial, const 
   }
 }
 
-// finalize + residual + RMSNorm of the result in one pass over the row (one CTA per stream):
+// finalize + residual + RMSNorm of the result in one pass over the row:
 //   out[m] = bf16(sum_s partial[s][m] + R[m]);  aux[m] = rmsnorm(out[m]) * w   (the NEXT op's pre-norm)
 // Replaces three kernels (finalize, residual add, RMSNorm) between a projection and the following GEMM.
-__global__ void skinny_finalize_norm_kernel(const float* __restrict__ partial, const __nv_bfloat16* __restrict__ R,
-                                            __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ w,
-                                            __nv_bfloat16* __restrict__ aux, int M, int N, int splits, float eps, int kyutai) {
+// A cluster of FIN_CL CTAs shares one row (M = 64 rows alone would leave most SMs idle): each CTA reduces its column
+// slice, the slice sums of squares are exchanged through distributed shared memory and added in rank order, so the
+// result does not depend on timing.
+constexpr int FIN_CL = 4;
+__global__ void __cluster_dims__(FIN_CL, 1, 1)
+skinny_finalize_norm_kernel(const float* __restrict__ partial, const __nv_bfloat16* __restrict__ R,
+                            __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ w,
+                            __nv_bfloat16* __restrict__ aux, int M, int N, int splits, float eps, int kyutai) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   __shared__ float red[32];
-  const int m = blockIdx.x;
+  __shared__ float slice_ss;
+  const int m = blockIdx.x / FIN_CL, slice = (int)cluster.block_rank();
+  const int n_lo = slice * (N / FIN_CL), n_hi = n_lo + N / FIN_CL;
   const long long MN = (long long)M * N;
   float ss = 0.f;
-  for (int n = threadIdx.x * 4; n < N; n += blockDim.x * 4) {
+  for (int n = n_lo + threadIdx.x * 4; n < n_hi; n += blockDim.x * 4) {
     const long long i = (long long)m * N + n;
     float4 v = *reinterpret_cast<const float4*>(partial + i);
     for (int s = 1; s < splits; ++s) {
@@ -186,12 +197,16 @@ __global__ void skinny_finalize_norm_kernel(const float* __restrict__ partial, c
   if (threadIdx.x < 32) {
     float t = threadIdx.x < blockDim.x / 32 ? red[threadIdx.x] : 0.f;
     t = warp_sum(t);
-    if (threadIdx.x == 0) red[0] = t;
+    if (threadIdx.x == 0) slice_ss = t;
   }
-  __syncthreads();
-  const float mean = red[0] / (float)N;
+  cluster.sync();
+  float tot = 0.f;
+#pragma unroll
+  for (int r = 0; r < FIN_CL; ++r) tot += *cluster.map_shared_rank(&slice_ss, r);
+  cluster.sync();   // nobody leaves (and frees its shared memory) while a peer may still be reading it
+  const float mean = tot / (float)N;
   const float r = kyutai ? rsqrtf(eps + mean) : rsqrtf(mean + eps);
-  for (int n = threadIdx.x * 4; n < N; n += blockDim.x * 4) {
+  for (int n = n_lo + threadIdx.x * 4; n < n_hi; n += blockDim.x * 4) {
     const long long i = (long long)m * N + n;
     const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(out + i);
     const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(w + n);
@@ -268,6 +283,7 @@ extern "C" int rstnet_skinny_gemm_create_fused(const void* X, const void* W, con
                                                rstnet_skinny_plan** outp) {
   RSTNET_REQUIRE(X && W && outp && (out || fin_mode == 2), "skinny_gemm_create: null pointer");
   RSTNET_REQUIRE(fin_mode >= 0 && fin_mode <= 2, "skinny_gemm_create: bad fin_mode");
+  RSTNET_REQUIRE(fin_mode != 1 || N % (4 * FIN_CL) == 0, "skinny_gemm_create: fused RMSNorm needs N %% 16 == 0 (N=%d)", N);
   RSTNET_REQUIRE(fin_mode == 0 || (partial_ws && aux_out && N % 4 == 0 && (fin_mode == 2 || norm_w)),
                  "skinny_gemm_create: fused finalize needs a workspace, an aux output and N %% 4 == 0");
   RSTNET_REQUIRE(M >= 1 && M <= 128 && N >= 1 && K >= SK_BK && K % SK_BK == 0, "skinny_gemm_create: need 1<=M<=128, K %% 64 == 0 (M=%d N=%d K=%d)", M, N, K);
@@ -330,7 +346,7 @@ extern "C" int rstnet_skinny_gemm_run(const rstnet_skinny_plan* pl, rstnet_strea
   if (int e = check_launch("gemm_skinny")) return e;
   const long long MN = (long long)pl->p.M * pl->p.N;
   if (pl->fin_mode == 1) {
-    skinny_finalize_norm_kernel<<<pl->p.M, 256, 0, st>>>(pl->p.partial, pl->p.R, pl->p.out, pl->norm_w, pl->aux, pl->p.M, pl->p.N,
+    skinny_finalize_norm_kernel<<<pl->p.M * FIN_CL, 256, 0, st>>>(pl->p.partial, pl->p.R, pl->p.out, pl->norm_w, pl->aux, pl->p.M, pl->p.N,
                                                          pl->p.splits, pl->eps, pl->kyutai);
     count_launch();
     return check_launch("skinny_finalize_norm");

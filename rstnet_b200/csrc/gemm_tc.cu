@@ -303,7 +303,8 @@ struct TsCfg {
   static constexpr int STAGE_BYTES = TC_A_BYTES + 2 * B_BYTES;
   static constexpr int STAGES = BN == 64 ? 5 : 6;
   static constexpr int OUT_LD = BN + 4;                       // padded row of the epilogue staging tile (floats)
-  static constexpr int OUT_BYTES = 4 * 32 * OUT_LD * 4;       // one 32-row slab per drain warp
+  static constexpr int BOXSET_BYTES = (BN / 32) * TC_BM * 128;   // [BN/32] swizzled [128 x 32] fp32 boxes of the TMA-store epilogue
+  static constexpr int OUT_BYTES = 4 * 32 * OUT_LD * 4;       // fallback transpose (one 32-row slab per drain warp); the box set fits inside
   static constexpr int CTRL_BYTES = 2048;                     // barriers (512) + bias/scale x2 (<= 1024), keeps the staging area 1024-aligned
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + CTRL_BYTES + OUT_BYTES;
   static constexpr int ACC_COLS = 2 * TC_NACC * BN;
@@ -566,13 +567,14 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (p.tma_store) {
         // Epilogue without per-thread global stores: the row (thread = TMEM lane) is finished in registers, written
         // into 128-byte-swizzled [128 x 32] boxes in shared memory and one thread issues TMA tile stores.  Two
-        // outputs (raw + ELU'd copy for the next layer) reuse the boxes after the first store has been read out.
-        uint8_t* boxes = reinterpret_cast<uint8_t*>(out_stage);   // [BN/32][128 rows][128 B], 1024-aligned
+        // outputs (raw + ELU'd copy for the next layer) reuse the boxes after the first store has been read out
+        // (a second box set was measured: no gain, and it pins the CTA at the 227 KB shared-memory limit).
         const uint32_t rsw = (uint32_t)(row * 128), rx = (uint32_t)(row & 7);
         const int nout = p.C2 ? 2 : 1;
         for (int oi = 0; oi < nout; ++oi) {
           const bool second = (nout == 2) && oi == 0;   // C2 first, C last
           const int act = second ? p.act2 : p.post_act;
+          uint8_t* boxes = reinterpret_cast<uint8_t*>(out_stage);   // [BN/32][128 rows][128 B], 1024-aligned
           if (!p.R) {
             if (dt == 0) bulk_wait_read0();             // earlier stores of this CTA no longer read the boxes
             named_bar_sync(2, 128);
