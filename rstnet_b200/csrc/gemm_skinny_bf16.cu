@@ -11,6 +11,7 @@
 #include <cuda_bf16.h>
 
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -297,7 +298,25 @@ extern "C" int rstnet_skinny_gemm_create_fused(const void* X, const void* W, con
   int splits = 1;
   RSTNET_REQUIRE(!(partial_ws && max_splits > 1) || N % 4 == 0, "skinny_gemm_create: split-K needs N %% 4 == 0");
   if (partial_ws && max_splits > 1) {
-    while (splits < max_splits && n_tiles * splits < 2 * 148 - 40 && kchunks / (splits * 2) >= 8) splits *= 2;
+    // Enough CTAs to keep ~1.5 per SM streaming, no more: every split adds an fp32 partial round trip.  Measured on
+    // the 7B shapes (scripts/skinny_sweep.py, GEMM + finalize, us): qkv 96 tiles {1: 30.7, 2: 28.9, 4: 36.7},
+    // fc 172 tiles {1: 48.1, 2: 53.4}, proj 32 tiles {2: 22.7, 4: 20.4, 8: 19.4}, mlp proj {4: 30.9, 6: 28.8, 8: 29.0}.
+    {
+      const int cand[6] = {1, 2, 3, 4, 6, 8};
+      const float want = 224.0f / (float)n_tiles;
+      float best = 1e30f;
+      for (int c : cand) {
+        if (c > max_splits || (c > 1 && kchunks / c < 8)) continue;
+        const float r = (float)c > want ? (float)c / want : want / (float)c;
+        if (r < best) { best = r; splits = c; }
+      }
+    }
+    if (const char* e = getenv("RSTNET_SKINNY_SPLITS")) {   // tuning aid (scripts/skinny_sweep.py)
+      const int v = atoi(e);
+      if (v >= 1 && v <= max_splits) splits = v;
+    }
+    // every split must own at least one K chunk (a CTA without work would never signal its accumulator)
+    while (splits > 1 && (splits - 1) * ceil_div(kchunks, splits) >= kchunks) --splits;
   }
   {
     cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)N};
