@@ -125,6 +125,97 @@ __global__ void ring_attention_kernel(const float* __restrict__ qkv, long long q
   }
 }
 
+
+// Two consecutive queries (2k, 2k+1) of one (b, h) per warp: a streaming step carries exactly one such pair per
+// stream (two 25 Hz tokens per 80 ms frame), and the pair shares every K / V row it reads -- at a full 250-token
+// context the fp32 ring (64 KB of K + 64 KB of V per (b, h)) is the HBM traffic of this kernel, so reading it once
+// instead of twice halves it.  Per query the arithmetic is the single-query kernel's (same block walk from the
+// pair's first key, same FMA order); a query that ends before the block gets zero weights there.
+__global__ void ring_attention_pair_kernel(const float* __restrict__ qkv, long long qbs, long long qts,
+                                           const float* __restrict__ kv, const long long* __restrict__ offset,
+                                           float* __restrict__ out, long long obs, long long ots, int B, int T, int H, int D,
+                                           int cap, int context, int linear) {
+  extern __shared__ __align__(16) float qs_all[];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int P = (T + 1) / 2;
+  const long long wid = (long long)blockIdx.x * (blockDim.x / 32) + warp;
+  const long long total = (long long)B * P * H;
+  float* qs0 = qs_all + warp * 2 * D;
+  float* qs1 = qs0 + D;
+  if (wid >= total) return;
+  const int h = (int)(wid % H);
+  const int t0 = 2 * (int)((wid / H) % P);
+  const int b = (int)(wid / ((long long)H * P));
+  const bool has1 = t0 + 1 < T;
+  {
+    const float* q0 = qkv + b * qbs + t0 * qts + h * D;
+    const float* q1 = has1 ? q0 + qts : q0;
+    for (int d = lane; d < D; d += 32) { qs0[d] = q0[d]; qs1[d] = q1[d]; }
+  }
+  __syncwarp();
+  const long long off = *offset;
+  const long long end = off + T;
+  const long long pos0 = off + t0, pos1 = has1 ? pos0 + 1 : pos0;
+  long long lo0 = pos0 - context + 1, lo1 = pos1 - context + 1;
+  if (lo0 < 0) lo0 = 0;
+  if (lo1 < 0) lo1 = 0;
+  if (!linear) {   // ring quirk, see ring_attention_kernel
+    if (lo0 < end - cap + 1) lo0 = end - cap + 1;
+    if (lo1 < end - cap + 1) lo1 = end - cap + 1;
+  }
+  const float* Kb = kv + ((long long)b * H + h) * cap * D;
+  const float* Vb = Kb + (long long)B * H * cap * D;
+  const float scale = 1.0f / sqrtf((float)D);
+  float m0 = -INFINITY, l0 = 0.f, m1 = -INFINITY, l1 = 0.f;
+  float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long p0 = lo0; p0 <= pos1; p0 += 32) {
+    const long long p = p0 + lane;
+    const bool in = p <= pos1;
+    const bool v0 = p <= pos0, v1 = in && p >= lo1;
+    const int slot = (int)((in ? p : pos1) % cap);
+    float s0 = -INFINITY, s1 = -INFINITY;
+    if (in) {
+      const float4* kp = reinterpret_cast<const float4*>(Kb + (long long)slot * D);
+      const float4* qa = reinterpret_cast<const float4*>(qs0);
+      const float4* qb = reinterpret_cast<const float4*>(qs1);
+      float d0 = 0.f, d1 = 0.f;
+      for (int d4 = 0; d4 < D / 4; ++d4) {
+        const float4 kk = kp[d4], a = qa[d4], c = qb[d4];
+        d0 = fmaf(a.x, kk.x, d0); d0 = fmaf(a.y, kk.y, d0); d0 = fmaf(a.z, kk.z, d0); d0 = fmaf(a.w, kk.w, d0);
+        d1 = fmaf(c.x, kk.x, d1); d1 = fmaf(c.y, kk.y, d1); d1 = fmaf(c.z, kk.z, d1); d1 = fmaf(c.w, kk.w, d1);
+      }
+      if (v0) s0 = d0 * scale;
+      if (v1) s1 = d1 * scale;
+    }
+    const float m0n = fmaxf(m0, warp_max(s0)), m1n = fmaxf(m1, warp_max(s1));
+    const float c0 = expf(m0 - m0n), c1 = expf(m1 - m1n);   // exp(-inf) = 0 on a query's first block
+    const float pj0 = v0 ? expf(s0 - m0n) : 0.f, pj1 = v1 ? expf(s1 - m1n) : 0.f;
+    l0 = l0 * c0 + warp_sum(pj0);
+    l1 = l1 * c1 + warp_sum(pj1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc0[i] *= c0; acc1[i] *= c1; }
+    const int nk = (int)min(32LL, pos1 - p0 + 1);
+    for (int j = 0; j < nk; ++j) {
+      const float w0 = __shfl_sync(0xffffffffu, pj0, j), w1 = __shfl_sync(0xffffffffu, pj1, j);
+      const int sj = __shfl_sync(0xffffffffu, slot, j);
+      const float* vp = Vb + (long long)sj * D;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int d = lane + 32 * i;
+        if (d < D) { const float vv = vp[d]; acc0[i] = fmaf(w0, vv, acc0[i]); acc1[i] = fmaf(w1, vv, acc1[i]); }
+      }
+    }
+    m0 = m0n; m1 = m1n;
+  }
+  float* o0 = out + b * obs + t0 * ots + h * D;
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int d = lane + 32 * i;
+    if (d < D) { o0[d] = acc0[i] * i0; if (has1) o0[ots + d] = acc1[i] * i1; }
+  }
+}
+
 }  // namespace rstnet
 using namespace rstnet;
 
@@ -149,11 +240,18 @@ extern "C" int rstnet_ring_attention_f32(const float* qkv, int64_t q_batch_strid
   RSTNET_REQUIRE(qkv && kv && offset && out, "ring_attention: null pointer");
   RSTNET_REQUIRE(batch > 0 && T > 0 && H > 0 && D > 0 && D % 4 == 0 && D <= 128 && cap > 0 && context > 0,
                  "ring_attention: bad shape (D %% 4 == 0 and D <= 128 required)");
-  const long long total = (long long)batch * T * H;
   const int warps = 4;
-  ring_attention_kernel<<<ceil_div(total, warps), warps * 32, warps * D * sizeof(float), (cudaStream_t)stream>>>(
-      qkv, q_batch_stride, q_time_stride, kv, (const long long*)offset, out, o_batch_stride, o_time_stride, batch, T, H, D,
-      cap, context, linear);
+  if (T >= 2) {
+    const long long total = (long long)batch * ((T + 1) / 2) * H;
+    ring_attention_pair_kernel<<<ceil_div(total, warps), warps * 32, warps * 2 * D * sizeof(float), (cudaStream_t)stream>>>(
+        qkv, q_batch_stride, q_time_stride, kv, (const long long*)offset, out, o_batch_stride, o_time_stride, batch, T, H, D,
+        cap, context, linear);
+  } else {
+    const long long total = (long long)batch * T * H;
+    ring_attention_kernel<<<ceil_div(total, warps), warps * 32, warps * D * sizeof(float), (cudaStream_t)stream>>>(
+        qkv, q_batch_stride, q_time_stride, kv, (const long long*)offset, out, o_batch_stride, o_time_stride, batch, T, H, D,
+        cap, context, linear);
+  }
   count_launch();
   return check_launch("ring_attention");
 }
