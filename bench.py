@@ -245,8 +245,12 @@ def run_ours(args):
 
     if rank == 0:
         roof = roofline_pass(m, x_dev, B, dev)
-        cpu_threads = best_cpu_threads()
-        cv, cdt = cpu_sample(8, 4, cpu_threads)
+        cpu = None
+        if world == 1:   # reported baseline: rank 0 at N = 1 only
+            cpu_threads = best_cpu_threads()
+            cv, cdt = cpu_sample(8, 4, cpu_threads)
+            cpu = {"value": cv, "unit": UNIT, "cores": cpu_threads, "host_cores": os.cpu_count(), "kind": "port",
+                   "sample": f"8 streams x 4 frames streaming encode+decode, torch CPU fp32 oracle port ({cdt:.1f} s)"}
         lm = None
         if world == 1 and not args.no_lm:
             m._stream_state = None
@@ -270,8 +274,7 @@ def run_ours(args):
             "gpu_launches": int(launches_per_frame * FRAMES * args.steps),
             "roofline": roof,
             "lm_decode": lm,
-            "cpu_baseline": {"value": cv, "unit": UNIT, "cores": cpu_threads, "host_cores": os.cpu_count(), "kind": "port",
-                             "sample": f"8 streams x 4 frames streaming encode+decode, torch CPU fp32 oracle port ({cdt:.1f} s)"},
+            "cpu_baseline": cpu,
         }
         print(json.dumps(line))
     if world > 1:

@@ -2,6 +2,8 @@
 // Follows StreamingMultiheadAttention.forward (modules/transformer.py:375-419), apply_rope
 // (modules/rope.py:11-68) and RingKVCache.complete (transformer.py:211-278) of the reference.
 // HBM/L2-bound gather work (0.05 GMAC per stream-second): CUDA cores, one warp per query.
+#include <cstdint>
+
 #include "common.cuh"
 #include "../../include/rstnet_b200.h"
 
@@ -216,6 +218,125 @@ __global__ void ring_attention_pair_kernel(const float* __restrict__ qkv, long l
   }
 }
 
+
+// head_dim 64 version of the pair kernel with coalesced traffic.  K: eight lanes share one key row (each lane owns eight
+// of the 64 dims, its two query slices live in registers), so a 128-bit load instruction covers four whole rows
+// instead of 32 different lines; the partial dots are reduced with three shuffles.  V: sixteen lanes cover one row with
+// 128-bit loads (two rows per instruction), the two half-warps accumulate alternate keys and are added at the end.
+// Ring slots advance incrementally (no per-key modulo).  At a 200-token context this kernel is 16 x 136 us of a
+// 256-stream frame in the one-row-per-lane form (launch list profiles/r1_codec_late_frame_launches.csv).
+__global__ void ring_attention_pair64_kernel(const float* __restrict__ qkv, long long qbs, long long qts,
+                                             const float* __restrict__ kv, const long long* __restrict__ offset,
+                                             float* __restrict__ out, long long obs, long long ots, int B, int T, int H,
+                                             int cap, int context, int linear) {
+  constexpr int D = 64;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int P = (T + 1) / 2;
+  const long long wid = (long long)blockIdx.x * (blockDim.x / 32) + warp;
+  if (wid >= (long long)B * P * H) return;
+  const int h = (int)(wid % H);
+  const int t0 = 2 * (int)((wid / H) % P);
+  const int b = (int)(wid / ((long long)H * P));
+  const bool has1 = t0 + 1 < T;
+  const int grp = lane >> 3, sub = lane & 7;       // K phase: key = 4 * it + grp, dims [8 sub, 8 sub + 8)
+  const int half = lane >> 4, vl = lane & 15;       // V phase: key = 2 * i + half, dims [4 vl, 4 vl + 4)
+  float qa[8], qb[8];
+  {
+    const float* q0 = qkv + b * qbs + t0 * qts + h * D + 8 * sub;
+    const float* q1 = has1 ? q0 + qts : q0;
+    const float4 a0 = *reinterpret_cast<const float4*>(q0), a1 = *reinterpret_cast<const float4*>(q0 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(q1), b1 = *reinterpret_cast<const float4*>(q1 + 4);
+    qa[0] = a0.x; qa[1] = a0.y; qa[2] = a0.z; qa[3] = a0.w; qa[4] = a1.x; qa[5] = a1.y; qa[6] = a1.z; qa[7] = a1.w;
+    qb[0] = b0.x; qb[1] = b0.y; qb[2] = b0.z; qb[3] = b0.w; qb[4] = b1.x; qb[5] = b1.y; qb[6] = b1.z; qb[7] = b1.w;
+  }
+  const long long off = *offset;
+  const long long end = off + T;
+  const long long pos0 = off + t0, pos1 = has1 ? pos0 + 1 : pos0;
+  long long lo0 = pos0 - context + 1, lo1 = pos1 - context + 1;
+  if (lo0 < 0) lo0 = 0;
+  if (lo1 < 0) lo1 = 0;
+  if (!linear) {   // ring quirk, see ring_attention_kernel
+    if (lo0 < end - cap + 1) lo0 = end - cap + 1;
+    if (lo1 < end - cap + 1) lo1 = end - cap + 1;
+  }
+  const float* Kb = kv + ((long long)b * H + h) * cap * D;
+  const float* Vb = Kb + (long long)B * H * cap * D;
+  const float scale = 0.125f;   // 1 / sqrt(64)
+  float m0 = -INFINITY, l0 = 0.f, m1 = -INFINITY, l1 = 0.f;
+  float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+  const int slot_last = (int)(pos1 % cap);
+  for (long long p0 = lo0; p0 <= pos1; p0 += 32) {
+    const int base = (int)(p0 % cap);
+    // ---- scores of the 32 keys of the block: lane holds keys 4 it + grp, it = 0..7
+    float s0[8], s1[8];
+    {
+      int slot = base + grp;
+      while (slot >= cap) slot -= cap;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const long long p = p0 + 4 * it + grp;
+        const bool in = p <= pos1;
+        const float* kr = Kb + (long long)(in ? slot : slot_last) * D + 8 * sub;
+        const float4 k0 = *reinterpret_cast<const float4*>(kr), k1 = *reinterpret_cast<const float4*>(kr + 4);
+        float d0 = qa[0] * k0.x, d1 = qb[0] * k0.x;
+        d0 = fmaf(qa[1], k0.y, d0); d0 = fmaf(qa[2], k0.z, d0); d0 = fmaf(qa[3], k0.w, d0);
+        d0 = fmaf(qa[4], k1.x, d0); d0 = fmaf(qa[5], k1.y, d0); d0 = fmaf(qa[6], k1.z, d0); d0 = fmaf(qa[7], k1.w, d0);
+        d1 = fmaf(qb[1], k0.y, d1); d1 = fmaf(qb[2], k0.z, d1); d1 = fmaf(qb[3], k0.w, d1);
+        d1 = fmaf(qb[4], k1.x, d1); d1 = fmaf(qb[5], k1.y, d1); d1 = fmaf(qb[6], k1.z, d1); d1 = fmaf(qb[7], k1.w, d1);
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) { d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); }
+        s0[it] = (p <= pos0) ? d0 * scale : -INFINITY;                 // p >= lo0 by construction
+        s1[it] = (in && p >= lo1) ? d1 * scale : -INFINITY;
+        slot += 4;
+        while (slot >= cap) slot -= cap;
+      }
+    }
+    float bm0 = s0[0], bm1 = s1[0];
+#pragma unroll
+    for (int it = 1; it < 8; ++it) { bm0 = fmaxf(bm0, s0[it]); bm1 = fmaxf(bm1, s1[it]); }
+    const float m0n = fmaxf(m0, warp_max(bm0)), m1n = fmaxf(m1, warp_max(bm1));
+    const float c0 = expf(m0 - m0n), c1 = expf(m1 - m1n);   // exp(-inf) = 0 on a query's first block
+    float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      s0[it] = s0[it] == -INFINITY ? 0.f : expf(s0[it] - m0n);
+      s1[it] = s1[it] == -INFINITY ? 0.f : expf(s1[it] - m1n);
+      ps0 += s0[it]; ps1 += s1[it];
+    }
+    if (sub != 0) { ps0 = 0.f; ps1 = 0.f; }   // the eight lanes of a group hold the same weights: count them once
+    l0 = l0 * c0 + warp_sum(ps0);
+    l1 = l1 * c1 + warp_sum(ps1);
+    acc0.x *= c0; acc0.y *= c0; acc0.z *= c0; acc0.w *= c0;
+    acc1.x *= c1; acc1.y *= c1; acc1.z *= c1; acc1.w *= c1;
+    // ---- P.V: half-warp `half` takes keys 2 i + half
+    const int nk = (int)min(32LL, pos1 - p0 + 1);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      // key j = 2 i + half lives at register index j / 4 of the lanes of group j % 4
+      const int src = (((2 * i) & 3) + half) << 3;
+      const float w0 = __shfl_sync(0xffffffffu, s0[i >> 1], src), w1 = __shfl_sync(0xffffffffu, s1[i >> 1], src);
+      const int j = 2 * i + half;
+      if (j < nk) {
+        int slot = base + j;
+        while (slot >= cap) slot -= cap;
+        const float4 vv = *reinterpret_cast<const float4*>(Vb + (long long)slot * D + 4 * vl);
+        acc0.x = fmaf(w0, vv.x, acc0.x); acc0.y = fmaf(w0, vv.y, acc0.y); acc0.z = fmaf(w0, vv.z, acc0.z); acc0.w = fmaf(w0, vv.w, acc0.w);
+        acc1.x = fmaf(w1, vv.x, acc1.x); acc1.y = fmaf(w1, vv.y, acc1.y); acc1.z = fmaf(w1, vv.z, acc1.z); acc1.w = fmaf(w1, vv.w, acc1.w);
+      }
+    }
+    m0 = m0n; m1 = m1n;
+  }
+  // even keys + odd keys
+  acc0.x += __shfl_xor_sync(0xffffffffu, acc0.x, 16); acc0.y += __shfl_xor_sync(0xffffffffu, acc0.y, 16);
+  acc0.z += __shfl_xor_sync(0xffffffffu, acc0.z, 16); acc0.w += __shfl_xor_sync(0xffffffffu, acc0.w, 16);
+  acc1.x += __shfl_xor_sync(0xffffffffu, acc1.x, 16); acc1.y += __shfl_xor_sync(0xffffffffu, acc1.y, 16);
+  acc1.z += __shfl_xor_sync(0xffffffffu, acc1.z, 16); acc1.w += __shfl_xor_sync(0xffffffffu, acc1.w, 16);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  float* o0 = out + b * obs + t0 * ots + h * D + 4 * vl;
+  if (half == 0) *reinterpret_cast<float4*>(o0) = make_float4(acc0.x * i0, acc0.y * i0, acc0.z * i0, acc0.w * i0);
+  else if (has1) *reinterpret_cast<float4*>(o0 + ots) = make_float4(acc1.x * i1, acc1.y * i1, acc1.z * i1, acc1.w * i1);
+}
+
 }  // namespace rstnet
 using namespace rstnet;
 
@@ -241,7 +362,14 @@ extern "C" int rstnet_ring_attention_f32(const float* qkv, int64_t q_batch_strid
   RSTNET_REQUIRE(batch > 0 && T > 0 && H > 0 && D > 0 && D % 4 == 0 && D <= 128 && cap > 0 && context > 0,
                  "ring_attention: bad shape (D %% 4 == 0 and D <= 128 required)");
   const int warps = 4;
-  if (T >= 2) {
+  const bool aligned16 = ((uintptr_t)qkv % 16) == 0 && ((uintptr_t)kv % 16) == 0 && ((uintptr_t)out % 16) == 0 && q_batch_stride % 4 == 0 &&
+                         q_time_stride % 4 == 0 && o_batch_stride % 4 == 0 && o_time_stride % 4 == 0;
+  if (T >= 2 && D == 64 && aligned16) {
+    const long long total = (long long)batch * ((T + 1) / 2) * H;
+    ring_attention_pair64_kernel<<<ceil_div(total, warps), warps * 32, 0, (cudaStream_t)stream>>>(
+        qkv, q_batch_stride, q_time_stride, kv, (const long long*)offset, out, o_batch_stride, o_time_stride, batch, T, H, cap,
+        context, linear);
+  } else if (T >= 2) {
     const long long total = (long long)batch * ((T + 1) / 2) * H;
     ring_attention_pair_kernel<<<ceil_div(total, warps), warps * 32, warps * 2 * D * sizeof(float), (cudaStream_t)stream>>>(
         qkv, q_batch_stride, q_time_stride, kv, (const long long*)offset, out, o_batch_stride, o_time_stride, batch, T, H, D,
