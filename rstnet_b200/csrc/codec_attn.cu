@@ -224,7 +224,7 @@ __global__ void ring_attention_pair_kernel(const float* __restrict__ qkv, long l
 // instead of 32 different lines; the partial dots are reduced with three shuffles.  V: sixteen lanes cover one row with
 // 128-bit loads (two rows per instruction), the two half-warps accumulate alternate keys and are added at the end.
 // Ring slots advance incrementally (no per-key modulo).  At a 200-token context this kernel is 16 x 136 us of a
-// 256-stream frame in the one-row-per-lane form (launch list profiles/r1_codec_late_frame_launches.csv).
+// 256-stream frame in the one-row-per-lane form (launch list profiles/r1_codec_late_frame_launches_rowperlane_attn.csv).
 __global__ void ring_attention_pair64_kernel(const float* __restrict__ qkv, long long qbs, long long qts,
                                              const float* __restrict__ kv, const long long* __restrict__ offset,
                                              float* __restrict__ out, long long obs, long long ots, int B, int T, int H,
