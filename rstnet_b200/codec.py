@@ -758,6 +758,7 @@ class _DecPlan(_Plan):
         self.add(lambda: ops.conv1d_cout1(last.t, last.bs, last.ts, eng.d_final_w, eng.d_final_b, wav, Lout, B, Lout, last.C,
                                           m.last_kernel_size))
         self.finish_streaming([qup, X] + a + (yda if self.tc else yd), F)
+        self.debug_bufs = {"qup": [qup], "X": [X], "a": a, "yd": yd, "yda": yda, "hd": hd_}   # scripts/diag_rows.py
 
     def run(self, codes: torch.Tensor, graphs: Optional[bool]) -> torch.Tensor:
         self.codes_in.copy_(codes)

@@ -304,7 +304,7 @@ struct TsCfg {
   static constexpr int STAGES = BN == 64 ? 5 : 6;
   static constexpr int OUT_LD = BN + 4;                       // padded row of the epilogue staging tile (floats)
   static constexpr int BOXSET_BYTES = (BN / 32) * TC_BM * 128;   // [BN/32] swizzled [128 x 32] fp32 boxes of the TMA-store epilogue
-  static constexpr int OUT_BYTES = 4 * 32 * OUT_LD * 4;       // fallback transpose (one 32-row slab per drain warp); the box set fits inside
+  static constexpr int OUT_BYTES = 2 * BOXSET_BYTES;          // two box sets (residual layers alternate per tile); the fallback transpose (4*32*OUT_LD*4) fits inside
   static constexpr int CTRL_BYTES = 2048;                     // barriers (512) + bias/scale x2 (<= 1024), keeps the staging area 1024-aligned
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + CTRL_BYTES + OUT_BYTES;
   static constexpr int ACC_COLS = 2 * TC_NACC * BN;
@@ -524,8 +524,12 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       else if (dt < 2 * BN) sb[dt] = (p.scale && n0 + dt - BN < p.N) ? p.scale[n0 + dt - BN] : 1.f;
       if (p.tma_store && p.R && dt == 0) {
         // residual tile -> epilogue boxes while the K loop runs (the boxes are free once the previous store was read out)
+        // Residual layers alternate between two box sets: the residual of tile t+1 is requested right after the store of
+        // tile t was issued, and a load landing in the boxes that store is still reading corrupted the tail rows of tile t
+        // (seen rarely, on cold GPUs, on the 64->128 1x1 conv of the 6 kHz decoder level -- scripts/diag_rows.py).  The
+        // wait below then only has to cover the store of tile t-1.
         bulk_wait_read0();
-        uint8_t* boxes = reinterpret_cast<uint8_t*>(out_stage);
+        uint8_t* boxes = reinterpret_cast<uint8_t*>(out_stage) + (ti & 1) * Cfg::BOXSET_BYTES;
         int nb = 0;
         for (int g8 = 0; g8 < BN / 32; ++g8) nb += (n0 + g8 * 32 < p.N) ? 1 : 0;
         mbar_arrive_expect_tx(r_full, (uint32_t)(nb * TC_BM * 128));
@@ -567,14 +571,15 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (p.tma_store) {
         // Epilogue without per-thread global stores: the row (thread = TMEM lane) is finished in registers, written
         // into 128-byte-swizzled [128 x 32] boxes in shared memory and one thread issues TMA tile stores.  Two
-        // outputs (raw + ELU'd copy for the next layer) reuse the boxes after the first store has been read out
-        // (a second box set was measured: no gain, and it pins the CTA at the 227 KB shared-memory limit).
+        // outputs (raw + ELU'd copy for the next layer) go through the two box sets, so neither store's source is rewritten
+        // within the tile.
         const uint32_t rsw = (uint32_t)(row * 128), rx = (uint32_t)(row & 7);
         const int nout = p.C2 ? 2 : 1;
         for (int oi = 0; oi < nout; ++oi) {
           const bool second = (nout == 2) && oi == 0;   // C2 first, C last
           const int act = second ? p.act2 : p.post_act;
-          uint8_t* boxes = reinterpret_cast<uint8_t*>(out_stage);   // [BN/32][128 rows][128 B], 1024-aligned
+          // [BN/32][128 rows][128 B] boxes, 1024-aligned; set 1 = odd tiles of residual layers / the second output of dual-output layers
+          uint8_t* boxes = reinterpret_cast<uint8_t*>(out_stage) + ((p.R ? (ti & 1) : oi) ? Cfg::BOXSET_BYTES : 0);
           if (!p.R) {
             if (dt == 0) bulk_wait_read0();             // earlier stores of this CTA no longer read the boxes
             named_bar_sync(2, 128);
