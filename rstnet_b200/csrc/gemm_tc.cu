@@ -343,8 +343,9 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const bool tr = p.trace && blockIdx.x == 0;
   if (timed) p.cta_times[blockIdx.x * 4 + 0] = gtime();
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  // A tile's K loop is padded to whole 4-stage chunks: the padding stages run the full barrier protocol (so the
-  // static slot / parity schedule holds) but move no data and issue no MMA.
+  // A tile's K loop is padded to whole 4-stage chunks.  A padding stage is an ordinary stage whose weight box lies past
+  // the end of K: TMA zero-fills it, so its MMAs add exactly 0 and no role needs a special case (a protocol-only variant
+  // of these stages was tried first and is the prime suspect for a rare wrong output tile on padded residual layers).
   const int total_k = p.taps * p.kchunks;
   const int kpad = (total_k + CH - 1) / CH * CH;
   const int nchunks = kpad / CH;
@@ -382,7 +383,6 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int s = (4 * V + u) % S;
           const uint32_t par = (uint32_t)(((4 * V + u) / S) & 1);
           mbar_wait(&empty[s], par ^ 1);
-          if (kit + u >= total_k) { mbar_arrive(&full[s]); continue; }   // padding stage
           if (tr && first_tile) p.trace[(kit + u) * 8 + 0] = clock64();
           uint8_t* st = smem + s * Cfg::STAGE_BYTES;
           mbar_arrive_expect_tx(&full[s], TC_A_BYTES + 2 * Cfg::B_BYTES);
@@ -431,12 +431,10 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (tr && first_tile) p.trace[(kit + u) * 8 + 3] = clock64();
           const uint32_t ah = a_tmem0 + (uint32_t)(u * 64), al = ah + 32u;
           const uint64_t db = desc0 + (uint64_t)((s * Cfg::STAGE_BYTES + TC_A_BYTES) >> 4);
-          if (kit + u < total_k) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              mma_tf32_ts(d0, ah + (uint32_t)(8 * k), db + (uint64_t)(2 * k), idesc2, (u == 0 && k == 0) ? 0u : 1u);
-              mma_tf32_ts(d1, al + (uint32_t)(8 * k), db + (uint64_t)(2 * k), idesc1, 1u);
-            }
+          for (int k = 0; k < 4; ++k) {
+            mma_tf32_ts(d0, ah + (uint32_t)(8 * k), db + (uint64_t)(2 * k), idesc2, (u == 0 && k == 0) ? 0u : 1u);
+            mma_tf32_ts(d1, al + (uint32_t)(8 * k), db + (uint64_t)(2 * k), idesc1, 1u);
           }
           tc_commit(&empty[s]);
           tc_commit(&a_free[u]);
@@ -475,14 +473,14 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int g = grp; g < my_total; g += 2, kit += 2) {
         if (kit >= kpad) kit -= kpad;
         const int s = g % S, sa = g % TS_NA;
-        mbar_wait(&full[s], (g / S) & 1);
-        if (kit >= total_k) {   // padding stage: nothing to convert
-          mbar_wait(&a_free[sa], ((g / TS_NA) & 1) ^ 1);
-          mbar_arrive(&a_ready[sa]);
-          continue;
-        }
-        if (tr && q == 0 && lane == 0 && g >= tr_ti * kpad && g < (tr_ti + 1) * kpad) p.trace[(g - tr_ti * kpad) * 8 + 1] = clock64();
+        // Order matters.  With an odd stage count the previous fill of slot s (stage g - S) belongs to the OTHER transform
+        // group, so this thread may get here before that fill has even landed; a parity wait on full[s] would then be
+        // satisfied by the phase before it and the tile would be read while the TMA for stage g is still in flight (seen as
+        // a rare wrong output tile on cold GPUs).  a_free of stage g - 4 implies the MMAs of stage g - S have retired, i.e.
+        // full[s] is in this stage's phase, so waiting for it second is exact.
         mbar_wait(&a_free[sa], ((g / TS_NA) & 1) ^ 1);
+        mbar_wait(&full[s], (g / S) & 1);
+        if (tr && q == 0 && lane == 0 && g >= tr_ti * kpad && g < (tr_ti + 1) * kpad) p.trace[(g - tr_ti * kpad) * 8 + 1] = clock64();
         tc_fence_after();
         const uint32_t base = smem0 + (uint32_t)(s * Cfg::STAGE_BYTES) + rowoff;
         uint32_t hi[32], lo[32];
@@ -580,8 +578,8 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int act = second ? p.act2 : p.post_act;
           // [BN/32][128 rows][128 B] boxes, 1024-aligned; set 1 = odd tiles of residual layers / the second output of dual-output layers
           uint8_t* boxes = reinterpret_cast<uint8_t*>(out_stage) + ((p.R ? (ti & 1) : oi) ? Cfg::BOXSET_BYTES : 0);
-          if (!p.R) {
-            if (dt == 0) bulk_wait_read0();             // earlier stores of this CTA no longer read the boxes
+          if (!p.R && oi == 0) {
+            if (dt == 0) bulk_wait_read0();             // the previous tile's stores no longer read either box set
             named_bar_sync(2, 128);
           }
           auto stage_rows = [&](auto act_c, auto res_c) {   // one instantiation per activation: only the executed one is fetched
