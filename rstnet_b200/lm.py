@@ -16,17 +16,16 @@ dtype recipe of `GPT(config).to(device, bfloat16)` (infer_no_streaming.py:104-10
 from __future__ import annotations
 
 import ctypes as C
-import math
 from contextlib import contextmanager
 from dataclasses import dataclass
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, Optional
 
 import torch
 from torch import nn
 
 from . import _lib, ops
 from ._lib import RstnetError
-from .codec import _Node, _register
+from .codec import _register
 
 
 @dataclass
