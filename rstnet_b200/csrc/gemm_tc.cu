@@ -344,8 +344,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (timed) p.cta_times[blockIdx.x * 4 + 0] = gtime();
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   // A tile's K loop is padded to whole 4-stage chunks.  A padding stage is an ordinary stage whose weight box lies past
-  // the end of K: TMA zero-fills it, so its MMAs add exactly 0 and no role needs a special case (a protocol-only variant
-  // of these stages was tried first and is the prime suspect for a rare wrong output tile on padded residual layers).
+  // the end of K: TMA zero-fills it, so its MMAs add exactly 0 and no role needs a special case.
   const int total_k = p.taps * p.kchunks;
   const int kpad = (total_k + CH - 1) / CH * CH;
   const int nchunks = kpad / CH;
