@@ -75,6 +75,10 @@ int rstnet_gemm_rows_f32(const rstnet_gemm_rows_args* args, rstnet_stream_t stre
  * Epilogue: post(R + scale*(acc + bias)); pre_act is applied to A in shared memory.
  * precision 0 = 3xTF32 split (fp32-equivalent, for RVQ-index exactness; W must already be rounded to
  * TF32 and W_lo = tf32(w - W) supplied -- see rstnet_tf32_split_f32), 1 = single TF32 pass.
+ * Precision 0 runs the persistent kernel (one CTA per SM walking the tiles, A operand through TMEM, TMA-store
+ * epilogue) when W_lo lies at a positive 16-byte-aligned distance after W, so that one 3-D descriptor reaches both --
+ * allocate them as one [2][N][K] tensor, as rstnet_b200/ops.py:tf32_split does; otherwise (and for precision 1) the
+ * one-CTA-per-tile kernel is used.  ELU in the persistent kernel's epilogue is evaluated with ex2.approx.
  * Same reference call sites as rstnet_gemm_rows_f32. */
 typedef struct rstnet_tc_plan rstnet_tc_plan;
 typedef struct {
@@ -100,9 +104,10 @@ typedef struct {
 int rstnet_tc_gemm_create(const rstnet_tc_gemm_desc* desc, rstnet_tc_plan** out);
 int rstnet_tc_gemm_run(const rstnet_tc_plan* plan, rstnet_stream_t stream);
 void rstnet_tc_gemm_destroy(rstnet_tc_plan* plan);
-/* profiling aid: CTA (0,0) writes clock64 stamps per k iteration to trace[taps*Kc/32][8]
- * (0 producer, 1 operands landed, 2 transformed, 3 MMA start, 4 MMA issued, 5/6 drain begin/end) */
-void rstnet_tc_gemm_set_trace(rstnet_tc_plan* plan, int64_t* trace, int64_t* cta_times /* [grid.x][4] globaltimer ns */);
+/* profiling aid: CTA 0 writes clock64 stamps per k iteration of one tile to trace[>= padded taps*Kc/32][8]
+ * (0 producer, 1 operands landed, 2 transformed, 3 MMA start, 4 MMA issued, 5/6 drain begin/end, column 7: epilogue);
+ * cta_times[max(grid.x, SM count)][4] globaltimer ns per CTA.  rstnet_tc_gemm_grid reports the tile grid (M x N tiles). */
+void rstnet_tc_gemm_set_trace(rstnet_tc_plan* plan, int64_t* trace, int64_t* cta_times);
 int rstnet_tc_gemm_grid(const rstnet_tc_plan* plan, int32_t* grid_x, int32_t* grid_y, int32_t* tile_n);
 /* hi[i] = tf32_rna(x[i]); lo[i] = tf32_rna(x[i] - hi[i])  (one-time weight preparation for precision 0) */
 int rstnet_tf32_split_f32(const float* x, float* hi, float* lo, int64_t n, rstnet_stream_t stream);
