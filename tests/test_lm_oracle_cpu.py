@@ -63,3 +63,18 @@ def test_product_gpt_state_dict_keys_and_token_ids():
     from rstnet_b200._lib import RstnetError
     with pytest.raises(RstnetError):
         m.streaming_forever(2)   # CPU / fp32: refused, no fallback
+
+
+def test_reverse_delay_matches_the_reference_rule():
+    """infer_no_streaming.py:311-323: codebook 0 keeps frames [0, L-1), codebooks 1..7 are shifted left by one frame;
+    an [L, 8] input is transposed first.  Checked against a direct restatement of that rule."""
+    from rstnet_b200.infer import reverse_delay
+    g = torch.Generator().manual_seed(3)
+    x = torch.randint(0, 2048, (8, 11), generator=g)
+    want = torch.ones_like(x)
+    want[0, :-1] = x[0, :-1]
+    want[1:, :-1] = x[1:, 1:]
+    want = want[:, :-1]
+    assert torch.equal(reverse_delay(x), want)
+    assert torch.equal(reverse_delay(x.t().contiguous()), want)
+    assert reverse_delay(x).shape == (8, 10)
