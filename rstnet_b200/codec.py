@@ -277,6 +277,21 @@ class MimiTokenizer:
         return wav.squeeze(1).detach().cpu()
 
 
+class MimiCodecBTK(MimiCodec):
+    """The AudioCodec-tree variant's token layout (AudioCodec/MimiCodec/models/MimiCodec.py:94-111 with
+    quantization/vq_dc.py:143-162): `encode` returns codes `[B, T, K]`, `decode` takes `[B, T, K]`.  A thin host-side
+    adapter over the same kernels; that variant's third-party quantizer itself is out of scope (SURVEY.md §8c:
+    `vector_quantize_pytorch` is not vendored, so the arithmetic follows the in-tree Kyutai RVQ)."""
+
+    def encode(self, audio_data: torch.Tensor) -> torch.Tensor:
+        return super().encode(audio_data).transpose(1, 2).contiguous()
+
+    def decode(self, codes: torch.Tensor) -> torch.Tensor:
+        if codes.dim() != 3:
+            raise RstnetError(f"codes must be [B, T, K], got {tuple(codes.shape)}")
+        return super().decode(codes.transpose(1, 2).contiguous())
+
+
 # ====================================================================== engine
 class _Buf:
     """fp32 activation buffer with `ctx` left-context rows: rows [ctx, ctx+T) are live, [0, ctx) is

@@ -141,3 +141,25 @@ def test_cabi_library_exports_every_declared_symbol():
         assert hasattr(L, s), f"{s} declared in include/rstnet_b200.h but not exported"
     assert sorted(_lib.SYMBOLS) == syms
     assert _lib.lib().rstnet_version() >= 100
+
+
+def test_btk_adapter_only_transposes(monkeypatch):
+    """MimiCodecBTK (AudioCodec-tree token layout [B, T, K]) must be a pure layout adapter around MimiCodec."""
+    from rstnet_b200 import codec as C
+    seen = {}
+
+    def fake_encode(self, audio):
+        return torch.arange(2 * 8 * 5).view(2, 8, 5)
+
+    def fake_decode(self, codes):
+        seen["codes"] = codes
+        return torch.zeros(codes.shape[0], 1, 1920 * codes.shape[2])
+
+    monkeypatch.setattr(C.MimiCodec, "encode", fake_encode)
+    monkeypatch.setattr(C.MimiCodec, "decode", fake_decode)
+    m = C.MimiCodecBTK(encoder_rates=[8, 6, 5, 4], codebook_size=2048, codebook_dim=256, rvq_layers=8)
+    btk = m.encode(torch.zeros(2, 1, 9600))
+    assert btk.shape == (2, 5, 8) and torch.equal(btk.transpose(1, 2), torch.arange(2 * 8 * 5).view(2, 8, 5))
+    wav = m.decode(btk)
+    assert seen["codes"].shape == (2, 8, 5) and torch.equal(seen["codes"], torch.arange(2 * 8 * 5).view(2, 8, 5))
+    assert wav.shape == (2, 1, 9600)
