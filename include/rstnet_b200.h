@@ -34,6 +34,12 @@ int rstnet_version(void);
 const char* rstnet_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t rstnet_launch_count(void);
+/* Sticky device-side error bits of the CURRENT device (the call synchronises it; clear != 0 resets them).
+ * Kernels cannot raise, so where the reference's ATen call would (nn.Embedding / F.embedding with an id outside the
+ * table, llama_streaming.py:505-517, core_vq.py:198-206; cos.index_select beyond block_size, llama_streaming.py:972-975)
+ * the kernel poisons its output row with NaN (or clamps, for RVQ codes) and sets: bit 0 (1) id / code out of range,
+ * bit 1 (2) RoPE position beyond the cos/sin tables. */
+uint32_t rstnet_device_error_flags(int clear);
 
 /* ---- strided-row GEMM: C[b,t,:] = post( R[b,t,:] + scale * (pre(A_row(b,t)) . Wt + bias) )
  * A_row(b,t) = K contiguous floats at A + b*a_batch_stride + t*a_row_stride.
@@ -143,16 +149,24 @@ int rstnet_convtr1d_depthwise_f32(const float* x, int64_t x_batch_stride, int64_
  * one step in a single launch); entry layout = rstnet_row_copy. */
 int rstnet_rows_fill_f32(float* buf, int64_t batch_stride, int32_t batch, int32_t C, int32_t row0,
                          int32_t nrows, int32_t mode, int32_t src_row, const int64_t* only_if_zero,
-                         rstnet_stream_t stream);
+                         int32_t only_if_zero_stride /* 0: one shared counter; 1: one per stream, stream of column c of
+                         batch b = b*(C/channels_per_stream) + c/channels_per_stream */,
+                         int32_t channels_per_stream, rstnet_stream_t stream);
 typedef struct {
   float* buf;
   int64_t batch_stride; /* elements */
   int32_t C, src_row, dst_row, nrows;
+  int32_t cps;          /* channels per stream within a row of C columns (0 -> C): which `active` flag governs a column */
+  int32_t reserved;
 } rstnet_row_copy;
+/* active (optional, device int64 [streams]): a stream whose flag is 0 keeps its carry rows -- the frame scheduler's
+ * "hold" for batch rows that received no input this tick (their state must not advance). */
 int rstnet_rows_copy_table_f32(const rstnet_row_copy* table_dev, int32_t n_entries, int32_t batch,
-                               rstnet_stream_t stream);
-/* offsets[i] += delta (device int64 counters: StreamingTransformer.offset, transformer.py:686-690) */
-int rstnet_counter_add(int64_t* counter, int64_t delta, rstnet_stream_t stream);
+                               const int64_t* active, rstnet_stream_t stream);
+/* counter[i] += delta for i < n (device int64 counters: StreamingTransformer.offset, transformer.py:686-690; one per
+ * stream so that a single stream can be reset / admitted while the others keep running) */
+int rstnet_counter_add(int64_t* counter, int64_t delta, int32_t n, const int64_t* active /* optional, [n]: 0 = hold */,
+                       rstnet_stream_t stream);
 
 /* ---- nn.LayerNorm over the last dim, eps inside sqrt (modules/transformer.py:113-114).
  * x row (b,t) at x + b*x_batch_stride + t*dim; y is contiguous [batch*rows_per_batch, dim]. */
@@ -166,15 +180,16 @@ int rstnet_layer_norm_f32(const float* x, int64_t x_batch_stride, const float* w
  * position (*offset + t), writes rotated q back in place and k,v into the ring kv[2][B][H][cap][D]
  * at slot (pos % cap).  Step 2 attends each query over keys with positions in
  * (pos_q - context, pos_q] that are still in the ring, fp32 softmax, out [B, T, H*D].
- * `offset` is a device int64 (positions already written before this call).  linear != 0: kv is a
+ * `offset` is a device int64 (positions already written before this call): one shared counter (offset_stride 0) or
+ * one per stream, offset[b] (offset_stride 1; streams admitted or reset at different times).  linear != 0: kv is a
  * plain [0, cap) buffer holding every position (non-streaming, KVCacheResult.from_kv); linear == 0:
  * ring semantics of RingKVCache.complete, including its quirk that the oldest slot (position
  * end - cap) is labelled `end_offset` and therefore masked once the ring has wrapped. */
 int rstnet_rope_kv_append_f32(float* qkv, int64_t q_batch_stride, int64_t q_time_stride, float* kv,
-                              const int64_t* offset, const float* freqs, int32_t batch, int32_t T,
-                              int32_t H, int32_t D, int32_t cap, rstnet_stream_t stream);
+                              const int64_t* offset, int32_t offset_stride, const float* freqs, int32_t batch,
+                              int32_t T, int32_t H, int32_t D, int32_t cap, rstnet_stream_t stream);
 int rstnet_ring_attention_f32(const float* qkv, int64_t q_batch_stride, int64_t q_time_stride,
-                              const float* kv, const int64_t* offset, float* out,
+                              const float* kv, const int64_t* offset, int32_t offset_stride, float* out,
                               int64_t o_batch_stride, int64_t o_time_stride, int32_t batch, int32_t T,
                               int32_t H, int32_t D, int32_t cap, int32_t context, int32_t linear,
                               rstnet_stream_t stream);
@@ -228,34 +243,48 @@ void rstnet_skinny_gemm_destroy(rstnet_skinny_plan* plan);
 /* ---- x[b] = sum_cb input_emb[cb][seq[b,cb+1]] + wte[seq[b,0]] with bf16 rounding after every add and
  * an exact zero row for id -1 (GPT.forward_global, llama_streaming.py:680-687; ScaledEmbedding :493-517).
  * seq: int64, row b at seq + b*seq_stride; tables_dev: device array of n_q table pointers. */
-int rstnet_lm_embed_sum_bf16(const int64_t* seq, int32_t seq_stride, const void* wte, const void* const* tables_dev,
-                             int32_t n_q, int32_t E, void* x, int32_t B, rstnet_stream_t stream);
-/* out[b] = table[ids[b*id_stride]] (zero row for id < 0): codecformer_text_emb / codecformer_emb (:738-742) */
-int rstnet_lm_embed_rows_bf16(const int64_t* ids, int32_t id_stride, const void* table, int32_t D, void* out, int32_t B,
-                              rstnet_stream_t stream);
+/* wte has wte_rows rows, every audio table table_rows rows; an id outside [-1, rows) -> NaN row + error bit 0. */
+int rstnet_lm_embed_sum_bf16(const int64_t* seq, int32_t seq_stride, const void* wte, int64_t wte_rows,
+                             const void* const* tables_dev, int64_t table_rows, int32_t n_q, int32_t E, void* x, int32_t rows,
+                             rstnet_stream_t stream);
+/* out[r] = table[ids[r*id_stride]] (zero row for id -1): codecformer_text_emb / codecformer_emb (:738-742) */
+int rstnet_lm_embed_rows_bf16(const int64_t* ids, int32_t id_stride, const void* table, int64_t table_rows, int32_t D,
+                              void* out, int32_t rows, rstnet_stream_t stream);
 /* ---- RMSNorm, fp32 inside.  kyutai == 0: lit_model.RMSNorm (lit_model.py:707-714);
  * kyutai != 0: modules/transformer.py:34-48 `_rms_norm` with dtype=float (eps added before the mean's rsqrt). */
 int rstnet_lm_rms_norm_bf16(const void* x, const void* w, void* y, int32_t rows, int32_t dim, float eps, int32_t kyutai,
                             rstnet_stream_t stream);
-/* ---- rotate-half RoPE with the model's bf16 cos/sin tables at row *offset, + ring-KV append
- * (lit_model.py:560-573, 620-634).  qkv [B][nh][3][hs] (litgpt interleave, llama_streaming.py:957-963);
- * q_out [B][nh*hs]; kv [2][B][nh][cap][hs]. */
-int rstnet_lm_rope_kv_append_bf16(const void* qkv, const void* cos_tab, const void* sin_tab, const int64_t* offset,
-                                  void* q_out, void* kv, int32_t B, int32_t nh, int32_t hs, int32_t cap,
+/* ---- rotate-half RoPE with the model's bf16 cos/sin tables [rope_rows][rope_n] (rope_n = rotary_percentage * hs
+ * leading dims rotate, llama_streaming.py:979-982) + ring-KV append (lit_model.py:560-573, 620-634).
+ * `rows` = Tn * B (time, stream) pairs, time-major: row r = tl*B + b is stream b at position *offset + tl (a decode step
+ * has Tn == 1; a prefill chunk several consecutive positions per stream).  qkv [rows][n_kv][n_head/n_kv + 2][hs] (litgpt
+ * per-group interleave, llama_streaming.py:952-963; n_kv == n_head is MHA); q_out [rows][n_head*hs];
+ * kv [2][B][n_kv][cap][hs] -- K/V are stored once per KV GROUP (the reference expands them to n_head copies before its
+ * cache, :965-967; the attention result is the same).  A position >= rope_rows -> NaN q/k + error bit 1. */
+int rstnet_lm_rope_kv_append_bf16(const void* qkv, const void* cos_tab, const void* sin_tab, int64_t rope_rows, int32_t rope_n,
+                                  const int64_t* offset, int32_t offset_stride /* 0 shared, 1 per stream */, void* q_out,
+                                  void* kv, int32_t rows, int32_t B, int32_t n_head, int32_t n_kv, int32_t hs, int32_t cap,
                                   rstnet_stream_t stream);
-/* ---- single-query attention over the ring with RingKVCache.complete's position labels and the
- * (pos_k>=0)&(delta>=0)&(delta<context) mask (llama_streaming.py:983-992), fp32 softmax. HBM-bound. */
-int rstnet_lm_ring_decode_attention_bf16(const void* q, const void* kv, const int64_t* offset, void* out, int32_t B,
-                                         int32_t nh, int32_t hs, int32_t cap, int32_t context, rstnet_stream_t stream);
+/* ---- one query position per row over the ring with RingKVCache.complete's position labels and the
+ * (pos_k>=0)&(delta>=0)&(delta<context) mask (llama_streaming.py:983-992), fp32 softmax. HBM-bound.  Rows as above;
+ * every position of the launch must already be in the ring and no slot a query needs may have been overwritten
+ * (callers keep *offset + Tn <= cap for Tn > 1). */
+int rstnet_lm_ring_decode_attention_bf16(const void* q, const void* kv, const int64_t* offset, int32_t offset_stride,
+                                         void* out, int32_t rows, int32_t B, int32_t n_head, int32_t n_kv, int32_t hs,
+                                         int32_t cap, int32_t context, rstnet_stream_t stream);
 /* out[m][c] = silu(ab[m][c]) * ab[m][I + c]   (LLaMAMLP / ActivationGating) */
 int rstnet_lm_silu_mul_bf16(const void* ab, void* out, int32_t M, int32_t I, rstnet_stream_t stream);
 /* ---- depth transformer attention at codebook step `step` (keys 0..step, capacity dep_q <= 8, no RoPE):
- * qkv [B][3][H][hd]; kvd [2][B][H][cap][hd] (modules/transformer.py:375-419 with weights_per_step). */
+ * qkv [B][3][H][hd]; kvd [2][B][H][cap][hd] (modules/transformer.py:375-419 with weights_per_step).
+ * ring_quirk != 0: streaming form (forward_codecformer, llama_streaming.py:727-749) -- RingKVCache.complete masks key 0
+ * on the last step; 0: non-streaming form (forward_local, :694-725; KVCacheResult.from_kv keeps every key). */
 int rstnet_lm_depth_attention_bf16(const void* qkv, void* kvd, void* out, int32_t B, int32_t H, int32_t hd, int32_t cap,
-                                   int32_t step, rstnet_stream_t stream);
+                                   int32_t step, int32_t ring_quirk, rstnet_stream_t stream);
 /* ---- sample_token / sample_token_audio[_2048] (utils/sampling.py:85-154): ids restricted to [0, n_valid);
- * top_k <= 0 -> argmax (first maximum); else top-k + temperature + exponential-noise multinomial with a
- * counter-based RNG keyed by (seed, *step_counter, row).  tokens[row*tok_stride] = id. */
+ * top_k == 0 -> argmax (first maximum; use_sampling False); 1 <= top_k <= 1024 -> top-k + temperature +
+ * exponential-noise multinomial (sample_top_k, :49-60); top_k < 0 -> temperature multinomial over all n_valid ids
+ * (sample_token with top_k == 0, :97-101).  Counter-based RNG keyed by (seed, *step_counter, row).
+ * tokens[row*tok_stride] = id. */
 int rstnet_lm_sample_bf16(const void* logits, int32_t rows, int32_t V, int32_t n_valid, int32_t top_k, float temp,
                           uint32_t seed, const int64_t* step_counter, int64_t* tokens, int32_t tok_stride,
                           rstnet_stream_t stream);

@@ -15,7 +15,7 @@ ACT_NONE, ACT_ELU, ACT_GELU = 0, 1, 2
 
 # every symbol include/rstnet_b200.h declares (tests assert the .so exports all of them)
 SYMBOLS = [
-    "rstnet_version", "rstnet_last_error", "rstnet_launch_count",
+    "rstnet_version", "rstnet_last_error", "rstnet_launch_count", "rstnet_device_error_flags",
     "rstnet_gemm_rows_f32", "rstnet_tc_gemm_create", "rstnet_tc_gemm_run", "rstnet_tc_gemm_destroy", "rstnet_tc_gemm_set_trace", "rstnet_tc_gemm_grid", "rstnet_tf32_split_f32", "rstnet_conv1d_cin1_f32", "rstnet_conv1d_cout1_f32",
     "rstnet_convtr1d_depthwise_f32", "rstnet_rows_fill_f32", "rstnet_rows_copy_table_f32",
     "rstnet_counter_add", "rstnet_layer_norm_f32", "rstnet_rope_kv_append_f32",
@@ -54,7 +54,7 @@ class TcGemmDesc(C.Structure):
 
 class RowCopy(C.Structure):
     _fields_ = [("buf", C.c_void_p), ("batch_stride", C.c_int64), ("C", C.c_int32), ("src_row", C.c_int32),
-                ("dst_row", C.c_int32), ("nrows", C.c_int32)]
+                ("dst_row", C.c_int32), ("nrows", C.c_int32), ("cps", C.c_int32), ("reserved", C.c_int32)]
 
 
 class RstnetError(RuntimeError):
@@ -73,6 +73,14 @@ def lib() -> C.CDLL:
         raise RstnetError(
             f"{LIB_PATH} not found: the CUDA extension is not built. Run `python -m rstnet_b200.build` "
             "(there is no CPU fallback).")
+    # a library built from other sources than the ones next to it would be driven through mismatched structs:
+    # compare the stamp the build wrote (git-ignored, like the .so) with the digest of the sources present
+    from . import build as _build
+    stamp = os.path.join(os.path.dirname(LIB_PATH), "build.sha256")
+    if os.path.isdir(_build.CSRC) and (not os.path.exists(stamp) or open(stamp).read().strip() != _build._digest()):
+        raise RstnetError(
+            f"{LIB_PATH} is stale (built from different sources than rstnet_b200/csrc + include/). "
+            "Run `python -m rstnet_b200.build`.")
     L = C.CDLL(LIB_PATH)
     vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
     L.rstnet_version.restype = C.c_int
@@ -90,12 +98,12 @@ def lib() -> C.CDLL:
     L.rstnet_conv1d_cin1_f32.argtypes = [vp, i64, i64, vp, vp, vp, vp, i64, i64, i32, i32, i32, i32, i32, i32, vp]
     L.rstnet_conv1d_cout1_f32.argtypes = [vp, i64, i64, vp, vp, vp, i64, i32, i32, i32, i32, vp]
     L.rstnet_convtr1d_depthwise_f32.argtypes = [vp, i64, i64, vp, vp, i64, i64, i32, i32, i32, i32, vp]
-    L.rstnet_rows_fill_f32.argtypes = [vp, i64, i32, i32, i32, i32, i32, i32, vp, vp]
-    L.rstnet_rows_copy_table_f32.argtypes = [vp, i32, i32, vp]
-    L.rstnet_counter_add.argtypes = [vp, i64, vp]
+    L.rstnet_rows_fill_f32.argtypes = [vp, i64, i32, i32, i32, i32, i32, i32, vp, i32, i32, vp]
+    L.rstnet_rows_copy_table_f32.argtypes = [vp, i32, i32, vp, vp]
+    L.rstnet_counter_add.argtypes = [vp, i64, i32, vp, vp]
     L.rstnet_layer_norm_f32.argtypes = [vp, i64, vp, vp, vp, i32, i32, i32, f32, vp]
-    L.rstnet_rope_kv_append_f32.argtypes = [vp, i64, i64, vp, vp, vp, i32, i32, i32, i32, i32, vp]
-    L.rstnet_ring_attention_f32.argtypes = [vp, i64, i64, vp, vp, vp, i64, i64, i32, i32, i32, i32, i32, i32, i32, vp]
+    L.rstnet_rope_kv_append_f32.argtypes = [vp, i64, i64, vp, vp, i32, vp, i32, i32, i32, i32, i32, vp]
+    L.rstnet_ring_attention_f32.argtypes = [vp, i64, i64, vp, vp, i32, vp, i64, i64, i32, i32, i32, i32, i32, i32, i32, vp]
     L.rstnet_rvq_encode_workspace.argtypes = [i64, i32, i32, i32]
     L.rstnet_rvq_encode_workspace.restype = i64
     L.rstnet_rvq_encode_f32.argtypes = [vp, i64, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, vp]
@@ -107,13 +115,15 @@ def lib() -> C.CDLL:
     L.rstnet_skinny_gemm_run.argtypes = [vp, vp]
     L.rstnet_skinny_gemm_destroy.argtypes = [vp]
     L.rstnet_skinny_gemm_destroy.restype = None
-    L.rstnet_lm_embed_sum_bf16.argtypes = [vp, i32, vp, vp, i32, i32, vp, i32, vp]
-    L.rstnet_lm_embed_rows_bf16.argtypes = [vp, i32, vp, i32, vp, i32, vp]
+    L.rstnet_lm_embed_sum_bf16.argtypes = [vp, i32, vp, i64, vp, i64, i32, i32, vp, i32, vp]
+    L.rstnet_lm_embed_rows_bf16.argtypes = [vp, i32, vp, i64, i32, vp, i32, vp]
+    L.rstnet_device_error_flags.argtypes = [i32]
+    L.rstnet_device_error_flags.restype = C.c_uint32
     L.rstnet_lm_rms_norm_bf16.argtypes = [vp, vp, vp, i32, i32, f32, i32, vp]
-    L.rstnet_lm_rope_kv_append_bf16.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
-    L.rstnet_lm_ring_decode_attention_bf16.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    L.rstnet_lm_rope_kv_append_bf16.argtypes = [vp, vp, vp, i64, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    L.rstnet_lm_ring_decode_attention_bf16.argtypes = [vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp]
     L.rstnet_lm_silu_mul_bf16.argtypes = [vp, vp, i32, i32, vp]
-    L.rstnet_lm_depth_attention_bf16.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    L.rstnet_lm_depth_attention_bf16.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]
     L.rstnet_lm_sample_bf16.argtypes = [vp, i32, i32, i32, i32, f32, C.c_uint32, vp, vp, i32, vp]
     for name in SYMBOLS:
         fn = getattr(L, name)

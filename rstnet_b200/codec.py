@@ -28,6 +28,21 @@ from . import ops
 from ._lib import ACT_ELU, ACT_GELU, ACT_NONE, RstnetError
 
 
+def on_own_device(fn):
+    """Run an API method with the module's CUDA device current: the C ABI launches on the calling thread's current
+    device, while the reference lets a model live on any device regardless of it."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **kw):
+        dev = self.device
+        if dev.type != "cuda" or torch.cuda.current_device() == (dev.index if dev.index is not None else torch.cuda.current_device()):
+            return fn(self, *a, **kw)
+        with torch.cuda.device(dev):
+            return fn(self, *a, **kw)
+    return wrapper
+
+
 class _Node(nn.Module):
     """Anonymous container so that parameters get the reference's dotted state_dict names."""
 
@@ -197,6 +212,7 @@ class MimiCodec(nn.Module):
 
     # ------------------------------------------------------------------ reference API
     @torch.no_grad()
+    @on_own_device
     def encode(self, audio_data: torch.Tensor) -> torch.Tensor:
         """[B,1,L] float -> codes [B,n_q,T] int64 (MimiCodec.py:93-101; MimiModel.encode when streaming)."""
         if audio_data.dim() != 3 or audio_data.shape[1] != 1:
@@ -208,6 +224,7 @@ class MimiCodec(nn.Module):
         return eng.encode_batch(x)
 
     @torch.no_grad()
+    @on_own_device
     def decode(self, codes: torch.Tensor) -> torch.Tensor:
         """codes [B,K,T] int -> wav [B,1,T*frame_size] float32 (MimiCodec.py:103-110)."""
         if codes.dim() != 3:
@@ -228,6 +245,7 @@ class MimiCodec(nn.Module):
     def is_streaming(self) -> bool:
         return self._stream_state is not None
 
+    @on_own_device
     def streaming_forever(self, batch_size: int):
         self._stream_state = _StreamState(self._eng(), batch_size)
 
@@ -239,10 +257,40 @@ class MimiCodec(nn.Module):
         finally:
             self._stream_state = None
 
-    def reset_streaming(self):
+    @on_own_device
+    def reset_streaming(self, streams=None):
+        """StreamingModule.reset_streaming (modules/streaming.py:115-126).  `streams` (an extension: the reference resets
+        all or nothing) restarts only those batch rows -- conv carries zeroed, transformer position counters back to 0 --
+        so a frame scheduler can admit a new stream into a free row of a live batch; the other rows, the buffers and the
+        captured CUDA graphs are untouched."""
         if self._stream_state is None:
             raise ValueError("Trying to reset streaming, but the codec wasn't streaming.")
-        self._stream_state.reset()
+        self._stream_state.reset(streams)
+
+    def set_active_streams(self, mask) -> None:
+        """Extension for batched serving: hold the streaming state of the rows whose flag is 0 during
+        the following encode / decode steps (a session that delivered no audio this tick keeps its exact state)."""
+        if self._stream_state is None:
+            raise ValueError("the codec is not streaming")
+        self._stream_state.set_active(mask)
+
+    def get_streaming_state(self):
+        """StreamingModule.get_streaming_state (modules/streaming.py:128-136): name -> state object.  The whole codec
+        is one streaming module here, so the dict has the single root entry; the object (conv carries, KV rings,
+        position counters, bound launch plans) is opaque and owned by the caller until it is set back."""
+        return {"": self._stream_state}
+
+    def set_streaming_state(self, state):
+        """StreamingModule.set_streaming_state (modules/streaming.py:138-151)."""
+        state = dict(state)
+        if "" not in state:
+            raise RuntimeError("Expected to find a streaming state for .")
+        st = state.pop("")
+        if state:
+            raise RuntimeError(f"Some states were not consumed: {list(state.keys())}")
+        if st is not None and (not isinstance(st, _StreamState) or st.eng is not self._eng()):
+            raise RuntimeError("the streaming state belongs to another codec (or to weights that were since reloaded / moved)")
+        self._stream_state = st
 
 
 class MimiTokenizer:
@@ -312,15 +360,20 @@ class _Buf:
     def off(self, row: int) -> int:
         return row * self.ts
 
-    def zero_ctx(self):
+    def zero_ctx(self, streams=None):
         if self.ctx:
-            (self.t[:self.ctx] if self.tbc else self.t[:, :self.ctx]).zero_()
+            if streams is None:
+                (self.t[:self.ctx] if self.tbc else self.t[:, :self.ctx]).zero_()
+            elif self.tbc:
+                self.t[:self.ctx, streams] = 0.0
+            else:
+                self.t[streams, :self.ctx] = 0.0
 
     def carry_entry(self):
         """row-copy table entry that moves the last ctx rows to the front (streaming carry)."""
         if self.tbc:
-            return (self.t, 0, self.B * self.C, self.T, 0, self.ctx)
-        return (self.t, self.bs, self.C, self.T, 0, self.ctx)
+            return (self.t, 0, self.B * self.C, self.T, 0, self.ctx, self.C)
+        return (self.t, self.bs, self.C, self.T, 0, self.ctx, self.C)
 
 
 class _Engine:
@@ -479,8 +532,9 @@ class _Plan:
     any batch / clip length).  tensor_cores=True: [rows, B, C] buffers + tcgen05 3xTF32 GEMM plans
     (streaming steps: every 128-row tile is 128 streams at one time step)."""
 
-    def __init__(self, eng: _Engine, B: int, streaming: bool, tensor_cores: bool):
+    def __init__(self, eng: _Engine, B: int, streaming: bool, tensor_cores: bool, active: Optional[torch.Tensor] = None):
         self.eng, self.B, self.streaming, self.tc = eng, B, streaming, tensor_cores
+        self.active = active   # [B] int64 flags shared by the scope's plans: 0 = hold this stream's state this step
         self.ops_list = []
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.precision = eng.m.decoder_precision if isinstance(self, _DecPlan) else eng.m.tc_precision
@@ -587,7 +641,7 @@ class _Plan:
         if self.streaming:
             cap = m.context
             kv = [torch.zeros(2, B, H, cap, hd, device=dev) for _ in range(m.num_layers)]
-            offset = torch.zeros(1, dtype=torch.int64, device=dev)
+            offset = torch.zeros(B, dtype=torch.int64, device=dev)   # one position counter per stream (per-stream reset)
         else:
             cap = F
             kv = [torch.zeros(2, B, H, cap, hd, device=dev)] * m.num_layers
@@ -622,21 +676,24 @@ class _Plan:
         table = ops.make_copy_table(entries, dev)
         n, nb = len(entries), (1 if self.tc else self.B)
         self.copy_table = table
-        self.add(lambda: ops.rows_copy_table(table, n, nb))
-        self.add(lambda: ops.counter_add(self.offset, F))
+        self.add(lambda: ops.rows_copy_table(table, n, nb, self.active))
+        self.add(lambda: ops.counter_add(self.offset, F, self.active))
 
-    def reset(self):
+    def reset(self, streams=None):
         assert self.streaming
         for b in self.carries:
-            b.zero_ctx()
-        self.offset.zero_()
+            b.zero_ctx(streams)
+        if streams is None:
+            self.offset.zero_()
+        else:
+            self.offset[streams] = 0
 
 
 class _EncPlan(_Plan):
     """Buffers + launch order of one encode pass (whole clip, or one streaming chunk)."""
 
-    def __init__(self, eng: _Engine, B: int, L: int, streaming: bool, tensor_cores: bool):
-        super().__init__(eng, B, streaming, tensor_cores)
+    def __init__(self, eng: _Engine, B: int, L: int, streaming: bool, tensor_cores: bool, active: Optional[torch.Tensor] = None):
+        super().__init__(eng, B, streaming, tensor_cores, active)
         m, dev = eng.m, eng.device
         self.L = L
         if streaming and L % m.frame_size != 0:
@@ -690,7 +747,8 @@ class _EncPlan(_Plan):
         # ConvDownsample1d: replicate padding (left on the first call only when streaming)
         fill_bs, fill_nb, fill_C = (0, 1, B * D) if self.tc else (X.bs, B, D)
         only0 = self.offset if streaming else None
-        self.add(lambda: ops.rows_fill(X.t, fill_bs, fill_nb, fill_C, 0, X.ctx, mode=1, src_row=X.ctx, only_if_zero=only0))
+        self.add(lambda: ops.rows_fill(X.t, fill_bs, fill_nb, fill_C, 0, X.ctx, mode=1, src_row=X.ctx, only_if_zero=only0,
+                                       channels_per_stream=D))
         if X.extra:
             self.add(lambda: ops.rows_fill(X.t, fill_bs, fill_nb, fill_C, X.ctx + X.T, X.extra, mode=1, src_row=X.ctx + X.T - 1))
         lat_buf = _LatView(lat, B, T5, D, self.tc)
@@ -724,8 +782,9 @@ class _LatView:
 class _DecPlan(_Plan):
     """Buffers + launch order of one decode pass."""
 
-    def __init__(self, eng: _Engine, B: int, T: int, streaming: bool, tensor_cores: bool, n_codes: Optional[int] = None):
-        super().__init__(eng, B, streaming, tensor_cores)
+    def __init__(self, eng: _Engine, B: int, T: int, streaming: bool, tensor_cores: bool, n_codes: Optional[int] = None,
+                 active: Optional[torch.Tensor] = None):
+        super().__init__(eng, B, streaming, tensor_cores, active)
         m, dev = eng.m, eng.device
         self.T = T
         D, nf = eng.D, eng.nf
@@ -808,6 +867,9 @@ class _StreamState:
         self.eng, self.B = eng, batch_size
         self.enc: Dict[int, _EncPlan] = {}
         self.dec: Dict[int, _DecPlan] = {}
+        # per-stream "advance" flags read by the carry copy and the position counters of every step (all ones unless a
+        # frame scheduler holds rows that received no input this tick, see set_active)
+        self.active = torch.ones(batch_size, dtype=torch.int64, device=eng.device)
 
     def encode(self, x: torch.Tensor) -> torch.Tensor:
         B, _, L = x.shape
@@ -818,7 +880,7 @@ class _StreamState:
         if L not in self.enc:
             if self.enc:
                 raise RstnetError("the chunk size must stay constant within one streaming scope")
-            self.enc[L] = _EncPlan(self.eng, B, L, True, self.eng.m.streaming_tensor_cores)
+            self.enc[L] = _EncPlan(self.eng, B, L, True, self.eng.m.streaming_tensor_cores, active=self.active)
         return self.enc[L].run(x, self.eng.m.use_cuda_graphs).clone()
 
     def decode(self, codes: torch.Tensor) -> torch.Tensor:
@@ -828,9 +890,22 @@ class _StreamState:
         if T not in self.dec:
             if self.dec:
                 raise RstnetError("the chunk size must stay constant within one streaming scope")
-            self.dec[T] = _DecPlan(self.eng, B, T, True, self.eng.m.streaming_tensor_cores, n_codes=K)
+            self.dec[T] = _DecPlan(self.eng, B, T, True, self.eng.m.streaming_tensor_cores, n_codes=K, active=self.active)
         return self.dec[T].run(codes, self.eng.m.use_cuda_graphs).clone()
 
-    def reset(self):
+    def set_active(self, mask):
+        """mask [B] (bool / int): streams with 0 are HELD by the next steps -- they still run through the kernels (the
+        batch is one launch sequence) but their conv carries and transformer positions do not advance, so the step
+        leaves no trace on them.  None = all streams advance."""
+        if mask is None:
+            self.active.fill_(1)
+        else:
+            self.active.copy_(torch.as_tensor(mask).to(device=self.eng.device, dtype=torch.int64).reshape(self.B))
+
+    def reset(self, streams=None):
+        if streams is not None:
+            streams = torch.as_tensor(streams, dtype=torch.int64, device=self.eng.device).reshape(-1)
+            if streams.numel() and (int(streams.min()) < 0 or int(streams.max()) >= self.B):
+                raise RstnetError(f"stream index outside [0, {self.B})")
         for p in list(self.enc.values()) + list(self.dec.values()):
-            p.reset()
+            p.reset(streams)

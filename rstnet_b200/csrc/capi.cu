@@ -31,6 +31,17 @@ int check_launch(const char* what) {
 
 }  // namespace rstnet
 
-extern "C" int rstnet_version(void) { return 100; }
+namespace rstnet {
+unsigned int lm_read_errors(bool clear);
+unsigned int rvq_read_errors(bool clear);
+}
+
+extern "C" int rstnet_version(void) { return 200; }
+// Sticky device-side error bits of the CURRENT device (synchronises it): 1 = token / code id outside its table,
+// 2 = RoPE position beyond the cos/sin tables.  Kernels cannot raise; they poison their output (NaN) and set a bit.
+extern "C" uint32_t rstnet_device_error_flags(int clear) {
+  cudaDeviceSynchronize();
+  return rstnet::lm_read_errors(clear != 0) | rstnet::rvq_read_errors(clear != 0);
+}
 extern "C" const char* rstnet_last_error(void) { return rstnet::g_err; }
 extern "C" int64_t rstnet_launch_count(void) { return rstnet::g_launches.load(); }

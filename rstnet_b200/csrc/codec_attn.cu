@@ -12,8 +12,8 @@ extern void count_launch();
 
 // one warp per (b, t, h); lanes stride over the D/2 rotation pairs
 __global__ void rope_kv_append_kernel(float* __restrict__ qkv, long long qbs, long long qts, float* __restrict__ kv,
-                                      const long long* __restrict__ offset, const float* __restrict__ freqs, int B, int T,
-                                      int H, int D, int cap) {
+                                      const long long* __restrict__ offset, int ostride, const float* __restrict__ freqs,
+                                      int B, int T, int H, int D, int cap) {
   const long long wid = (long long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   const long long total = (long long)B * T * H;
@@ -21,7 +21,8 @@ __global__ void rope_kv_append_kernel(float* __restrict__ qkv, long long qbs, lo
   const int h = (int)(wid % H);
   const int t = (int)((wid / H) % T);
   const int b = (int)(wid / ((long long)H * T));
-  const long long pos = *offset + t;
+  const long long off = offset[(long long)b * ostride];   // per-stream position counters (ostride 1) or one shared (0)
+  const long long pos = off + t;
   const int slot = (int)(pos % cap);
   const int HD = H * D;
   float* q = qkv + b * qbs + t * qts + h * D;
@@ -30,7 +31,7 @@ __global__ void rope_kv_append_kernel(float* __restrict__ qkv, long long qbs, lo
   float* kdst = kv + (((long long)b * H + h) * cap + slot) * D;
   float* vdst = kv + (long long)B * H * cap * D + (((long long)b * H + h) * cap + slot) * D;
   // ts = offset.float() + arange(T) in fp32 (rope.py:39)
-  const float ts = __fadd_rn((float)(*offset), (float)t);
+  const float ts = __fadd_rn((float)off, (float)t);
   for (int pr = lane; pr < D / 2; pr += 32) {
     const float ang = __fmul_rn(freqs[pr], ts);
     const float c = cosf(ang), s = sinf(ang);
@@ -49,7 +50,7 @@ __global__ void rope_kv_append_kernel(float* __restrict__ qkv, long long qbs, lo
 // one warp per (b, h, tq): lane j scores key j of each 32-key block, online softmax, then the
 // lanes own output dims (lane, lane+32, ...) for the P.V accumulation (coalesced V reads).
 __global__ void ring_attention_kernel(const float* __restrict__ qkv, long long qbs, long long qts,
-                                      const float* __restrict__ kv, const long long* __restrict__ offset,
+                                      const float* __restrict__ kv, const long long* __restrict__ offset, int ostride,
                                       float* __restrict__ out, long long obs, long long ots, int B, int T, int H, int D, int cap,
                                       int context, int linear) {
   extern __shared__ __align__(16) float qs_all[];
@@ -68,7 +69,7 @@ __global__ void ring_attention_kernel(const float* __restrict__ qkv, long long q
   }
   __syncwarp();
   if (!active) return;
-  const long long off = *offset;
+  const long long off = offset[(long long)b * ostride];
   const long long end = off + T;
   const long long pos_q = off + t;
   long long lo = pos_q - context + 1;
@@ -134,7 +135,7 @@ __global__ void ring_attention_kernel(const float* __restrict__ qkv, long long q
 // instead of twice halves it.  Per query the arithmetic is the single-query kernel's (same block walk from the
 // pair's first key, same FMA order); a query that ends before the block gets zero weights there.
 __global__ void ring_attention_pair_kernel(const float* __restrict__ qkv, long long qbs, long long qts,
-                                           const float* __restrict__ kv, const long long* __restrict__ offset,
+                                           const float* __restrict__ kv, const long long* __restrict__ offset, int ostride,
                                            float* __restrict__ out, long long obs, long long ots, int B, int T, int H, int D,
                                            int cap, int context, int linear) {
   extern __shared__ __align__(16) float qs_all[];
@@ -155,7 +156,7 @@ __global__ void ring_attention_pair_kernel(const float* __restrict__ qkv, long l
     for (int d = lane; d < D; d += 32) { qs0[d] = q0[d]; qs1[d] = q1[d]; }
   }
   __syncwarp();
-  const long long off = *offset;
+  const long long off = offset[(long long)b * ostride];
   const long long end = off + T;
   const long long pos0 = off + t0, pos1 = has1 ? pos0 + 1 : pos0;
   long long lo0 = pos0 - context + 1, lo1 = pos1 - context + 1;
@@ -226,7 +227,7 @@ __global__ void ring_attention_pair_kernel(const float* __restrict__ qkv, long l
 // Ring slots advance incrementally (no per-key modulo).  At a 200-token context this kernel is 16 x 136 us of a
 // 256-stream frame in the one-row-per-lane form (launch list profiles/r1_codec_late_frame_launches_rowperlane_attn.csv).
 __global__ void ring_attention_pair64_kernel(const float* __restrict__ qkv, long long qbs, long long qts,
-                                             const float* __restrict__ kv, const long long* __restrict__ offset,
+                                             const float* __restrict__ kv, const long long* __restrict__ offset, int ostride,
                                              float* __restrict__ out, long long obs, long long ots, int B, int T, int H,
                                              int cap, int context, int linear) {
   constexpr int D = 64;
@@ -249,7 +250,7 @@ __global__ void ring_attention_pair64_kernel(const float* __restrict__ qkv, long
     qa[0] = a0.x; qa[1] = a0.y; qa[2] = a0.z; qa[3] = a0.w; qa[4] = a1.x; qa[5] = a1.y; qa[6] = a1.z; qa[7] = a1.w;
     qb[0] = b0.x; qb[1] = b0.y; qb[2] = b0.z; qb[3] = b0.w; qb[4] = b1.x; qb[5] = b1.y; qb[6] = b1.z; qb[7] = b1.w;
   }
-  const long long off = *offset;
+  const long long off = offset[(long long)b * ostride];
   const long long end = off + T;
   const long long pos0 = off + t0, pos1 = has1 ? pos0 + 1 : pos0;
   long long lo0 = pos0 - context + 1, lo1 = pos1 - context + 1;
@@ -341,23 +342,24 @@ __global__ void ring_attention_pair64_kernel(const float* __restrict__ qkv, long
 using namespace rstnet;
 
 extern "C" int rstnet_rope_kv_append_f32(float* qkv, int64_t q_batch_stride, int64_t q_time_stride, float* kv,
-                                         const int64_t* offset, const float* freqs, int32_t batch, int32_t T, int32_t H,
-                                         int32_t D, int32_t cap, rstnet_stream_t stream) {
+                                         const int64_t* offset, int32_t offset_stride, const float* freqs, int32_t batch,
+                                         int32_t T, int32_t H, int32_t D, int32_t cap, rstnet_stream_t stream) {
   RSTNET_REQUIRE(qkv && kv && offset && freqs, "rope_kv_append: null pointer");
   RSTNET_REQUIRE(batch > 0 && T > 0 && H > 0 && D > 0 && D % 2 == 0 && cap > 0, "rope_kv_append: bad shape");
   RSTNET_REQUIRE(T <= cap, "rope_kv_append: T (%d) exceeds ring capacity (%d)", T, cap);
   const long long total = (long long)batch * T * H;
   const int warps = 8;
   rope_kv_append_kernel<<<ceil_div(total, warps), warps * 32, 0, (cudaStream_t)stream>>>(
-      qkv, q_batch_stride, q_time_stride, kv, (const long long*)offset, freqs, batch, T, H, D, cap);
+      qkv, q_batch_stride, q_time_stride, kv, (const long long*)offset, offset_stride ? 1 : 0, freqs, batch, T, H, D, cap);
   count_launch();
   return check_launch("rope_kv_append");
 }
 
 extern "C" int rstnet_ring_attention_f32(const float* qkv, int64_t q_batch_stride, int64_t q_time_stride, const float* kv,
-                                         const int64_t* offset, float* out, int64_t o_batch_stride, int64_t o_time_stride,
-                                         int32_t batch, int32_t T, int32_t H, int32_t D, int32_t cap, int32_t context,
-                                         int32_t linear, rstnet_stream_t stream) {
+                                         const int64_t* offset, int32_t offset_stride, float* out, int64_t o_batch_stride,
+                                         int64_t o_time_stride, int32_t batch, int32_t T, int32_t H, int32_t D, int32_t cap,
+                                         int32_t context, int32_t linear, rstnet_stream_t stream) {
+  const int ostride = offset_stride ? 1 : 0;
   RSTNET_REQUIRE(qkv && kv && offset && out, "ring_attention: null pointer");
   RSTNET_REQUIRE(batch > 0 && T > 0 && H > 0 && D > 0 && D % 4 == 0 && D <= 128 && cap > 0 && context > 0,
                  "ring_attention: bad shape (D %% 4 == 0 and D <= 128 required)");
@@ -367,17 +369,17 @@ extern "C" int rstnet_ring_attention_f32(const float* qkv, int64_t q_batch_strid
   if (T >= 2 && D == 64 && aligned16) {
     const long long total = (long long)batch * ((T + 1) / 2) * H;
     ring_attention_pair64_kernel<<<ceil_div(total, warps), warps * 32, 0, (cudaStream_t)stream>>>(
-        qkv, q_batch_stride, q_time_stride, kv, (const long long*)offset, out, o_batch_stride, o_time_stride, batch, T, H, cap,
+        qkv, q_batch_stride, q_time_stride, kv, (const long long*)offset, ostride, out, o_batch_stride, o_time_stride, batch, T, H, cap,
         context, linear);
   } else if (T >= 2) {
     const long long total = (long long)batch * ((T + 1) / 2) * H;
     ring_attention_pair_kernel<<<ceil_div(total, warps), warps * 32, warps * 2 * D * sizeof(float), (cudaStream_t)stream>>>(
-        qkv, q_batch_stride, q_time_stride, kv, (const long long*)offset, out, o_batch_stride, o_time_stride, batch, T, H, D,
+        qkv, q_batch_stride, q_time_stride, kv, (const long long*)offset, ostride, out, o_batch_stride, o_time_stride, batch, T, H, D,
         cap, context, linear);
   } else {
     const long long total = (long long)batch * T * H;
     ring_attention_kernel<<<ceil_div(total, warps), warps * 32, warps * D * sizeof(float), (cudaStream_t)stream>>>(
-        qkv, q_batch_stride, q_time_stride, kv, (const long long*)offset, out, o_batch_stride, o_time_stride, batch, T, H, D,
+        qkv, q_batch_stride, q_time_stride, kv, (const long long*)offset, ostride, out, o_batch_stride, o_time_stride, batch, T, H, D,
         cap, context, linear);
   }
   count_launch();

@@ -112,32 +112,48 @@ __global__ void convtr_depthwise_kernel(const float* __restrict__ x, long long x
 }
 
 // ---------------------------------------------------------------- row fill / carry copy
+// only_if_zero: per-stream counters when oz_stride == 1 (stream of column c in batch b = b * (C / cps) + c / cps,
+// cps = channels per stream: the batch-major layout has C == cps, the time-major one C == B * cps), one shared counter
+// when oz_stride == 0.
 __global__ void rows_fill_kernel(float* __restrict__ buf, long long bs, int C, int row0, int nrows, int mode,
-                                 int src_row, const long long* __restrict__ only_if_zero) {
-  if (only_if_zero && *only_if_zero != 0) return;
+                                 int src_row, const long long* __restrict__ only_if_zero, int oz_stride, int cps) {
+  if (only_if_zero && !oz_stride && *only_if_zero != 0) return;
   const int b = blockIdx.y;
   float* bb = buf + (long long)b * bs;
   const long long total = (long long)nrows * C;
+  const int spb = C / cps;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
+    if (only_if_zero && oz_stride && only_if_zero[(long long)b * spb + c / cps] != 0) continue;
     bb[(long long)row0 * C + i] = mode == 1 ? bb[(long long)src_row * C + c] : 0.f;
   }
 }
 
 // Each thread owns one channel column and moves its rows in ascending order, so a carry that is
 // longer than the chunk (src and dst row ranges overlap, src_row >= dst_row) still shifts correctly.
-__global__ void rows_copy_table_kernel(const rstnet_row_copy* __restrict__ table, int n_entries) {
+// active (optional): one flag per stream; a stream whose flag is 0 keeps its carry rows (a frame scheduler "holds" the
+// rows that had no input this tick: their state must not advance).  Stream of column c of batch b =
+// b * (C / cps) + c / cps with cps = the entry's channels per stream (0 -> C).
+__global__ void rows_copy_table_kernel(const rstnet_row_copy* __restrict__ table, int n_entries,
+                                       const long long* __restrict__ active) {
   const int e = blockIdx.y, b = blockIdx.z;
   if (e >= n_entries) return;
   const rstnet_row_copy ent = table[e];
   float* bb = ent.buf + (long long)b * ent.batch_stride;
   const float* src = bb + (long long)ent.src_row * ent.C;
   float* dst = bb + (long long)ent.dst_row * ent.C;
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ent.C; c += gridDim.x * blockDim.x)
+  const int cps = ent.cps > 0 ? ent.cps : ent.C;
+  const int spb = ent.C / cps;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ent.C; c += gridDim.x * blockDim.x) {
+    if (active && active[(long long)b * spb + c / cps] == 0) continue;
     for (int r = 0; r < ent.nrows; ++r) dst[(long long)r * ent.C + c] = src[(long long)r * ent.C + c];
+  }
 }
 
-__global__ void counter_add_kernel(long long* c, long long d) { *c += d; }
+__global__ void counter_add_kernel(long long* c, long long d, int n, const long long* __restrict__ active) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    if (!active || active[i] != 0) c[i] += d;
+}
 
 // ---------------------------------------------------------------- LayerNorm: one warp per row
 __global__ void layer_norm_kernel(const float* __restrict__ x, long long xbs, const float* __restrict__ w,
@@ -183,8 +199,8 @@ extern "C" int rstnet_conv1d_cout1_f32(const float* x, int64_t xbs, int64_t xts,
   const int warps = 4;
   const size_t smem = ((size_t)k * Cin + (size_t)warps * (32 + k - 1) * (Cin + 1)) * sizeof(float);
   RSTNET_REQUIRE(smem <= 200 * 1024, "conv1d_cout1: Cin*k too large for shared memory");
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(conv_cout1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  static unsigned long long attr = 0;
+  smem_optin(conv_cout1_kernel, 200 * 1024, attr);
   dim3 grid((unsigned)ceil_div(T, 32 * warps), (unsigned)batch);
   conv_cout1_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(x, xbs, xts, w, bias, out, obs, T, Cin, k);
   count_launch();
@@ -205,33 +221,37 @@ extern "C" int rstnet_convtr1d_depthwise_f32(const float* x, int64_t xbs, int64_
 }
 
 extern "C" int rstnet_rows_fill_f32(float* buf, int64_t bs, int32_t batch, int32_t C, int32_t row0, int32_t nrows,
-                                    int32_t mode, int32_t src_row, const int64_t* only_if_zero,
-                                    rstnet_stream_t stream) {
+                                    int32_t mode, int32_t src_row, const int64_t* only_if_zero, int32_t only_if_zero_stride,
+                                    int32_t channels_per_stream, rstnet_stream_t stream) {
   RSTNET_REQUIRE(buf, "rows_fill: null pointer");
+  if (channels_per_stream <= 0) channels_per_stream = C;
+  RSTNET_REQUIRE(C % channels_per_stream == 0, "rows_fill: C (%d) must be a multiple of channels_per_stream (%d)", C, channels_per_stream);
   if (nrows <= 0 || batch <= 0) return 0;
   const long long total = (long long)nrows * C;
   int gx = ceil_div(total, 256);
   if (gx > 1024) gx = 1024;
   rows_fill_kernel<<<dim3(gx, batch), 256, 0, (cudaStream_t)stream>>>(buf, bs, C, row0, nrows, mode, src_row,
-                                                                     (const long long*)only_if_zero);
+                                                                     (const long long*)only_if_zero, only_if_zero_stride ? 1 : 0,
+                                                                     channels_per_stream);
   count_launch();
   return check_launch("rows_fill");
 }
 
 extern "C" int rstnet_rows_copy_table_f32(const rstnet_row_copy* table_dev, int32_t n_entries, int32_t batch,
-                                          rstnet_stream_t stream) {
+                                          const int64_t* active, rstnet_stream_t stream) {
   RSTNET_REQUIRE(table_dev, "rows_copy_table: null pointer");
   if (n_entries <= 0 || batch <= 0) return 0;
   RSTNET_REQUIRE(n_entries <= 65535 && batch <= 65535, "rows_copy_table: too many entries / batch");
   // grid.x strides over the channel columns of an entry (up to batch*C in the time-major layout)
-  rows_copy_table_kernel<<<dim3(batch > 1 ? 4 : 256, n_entries, batch), 256, 0, (cudaStream_t)stream>>>(table_dev, n_entries);
+  rows_copy_table_kernel<<<dim3(batch > 1 ? 4 : 256, n_entries, batch), 256, 0, (cudaStream_t)stream>>>(table_dev, n_entries,
+                                                                                                          (const long long*)active);
   count_launch();
   return check_launch("rows_copy_table");
 }
 
-extern "C" int rstnet_counter_add(int64_t* counter, int64_t delta, rstnet_stream_t stream) {
-  RSTNET_REQUIRE(counter, "counter_add: null pointer");
-  counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((long long*)counter, delta);
+extern "C" int rstnet_counter_add(int64_t* counter, int64_t delta, int32_t n, const int64_t* active, rstnet_stream_t stream) {
+  RSTNET_REQUIRE(counter && n >= 1, "counter_add: bad argument");
+  counter_add_kernel<<<1, n >= 256 ? 256 : 32, 0, (cudaStream_t)stream>>>((long long*)counter, delta, n, (const long long*)active);
   count_launch();
   return check_launch("counter_add");
 }

@@ -76,4 +76,17 @@ __device__ __forceinline__ float warp_max(float v) {
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// One-time opt-in to more than 48 KB of dynamic shared memory.  The attribute belongs to the (function, device) pair, so
+// the "done" mask is keyed by the CURRENT device ordinal: a second GPU in the same process gets its own opt-in.
+template <typename Kernel>
+inline void smem_optin(Kernel* kernel, int bytes, unsigned long long& done_mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(done_mask & bit)) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    done_mask |= bit;
+  }
+}
+
 }  // namespace rstnet

@@ -204,11 +204,8 @@ __global__ void __launch_bounds__(Cfg::NT) gemm_rows_kernel(const rstnet_gemm_ro
 
 template <class Cfg>
 static int launch_cfg(const rstnet_gemm_rows_args& a, cudaStream_t st) {
-  static bool attr_done = false;  // per instantiation; benign if raced
-  if (!attr_done) {
-    cudaFuncSetAttribute(gemm_rows_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    attr_done = true;
-  }
+  static unsigned long long attr_done = 0;  // per instantiation and per device; benign if raced
+  smem_optin(gemm_rows_kernel<Cfg>, Cfg::SMEM_BYTES, attr_done);
   const long long M = (long long)a.batch * a.rows;
   dim3 grid((unsigned)ceil_div(M, Cfg::BM), (unsigned)ceil_div(a.N, Cfg::BN));
   gemm_rows_kernel<Cfg><<<grid, Cfg::NT, Cfg::SMEM_BYTES, st>>>(a);

@@ -354,11 +354,8 @@ extern "C" int rstnet_skinny_gemm_create_fused(const void* X, const void* W, con
 
 extern "C" int rstnet_skinny_gemm_run(const rstnet_skinny_plan* pl, rstnet_stream_t stream) {
   RSTNET_REQUIRE(pl != nullptr, "skinny_gemm_run: null plan");
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(gemm_skinny_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr = true;
-  }
+  static unsigned long long attr = 0;
+  smem_optin(gemm_skinny_kernel<4>, 200 * 1024, attr);
   cudaStream_t st = (cudaStream_t)stream;
   gemm_skinny_kernel<4><<<pl->grid, SK_THREADS, pl->smem, st>>>(pl->tmW, pl->tmX, pl->p);
   count_launch();

@@ -730,11 +730,8 @@ struct rstnet_tc_plan {
 template <int BN>
 static int tc_launch_ts(const rstnet_tc_plan* pl, cudaStream_t st) {
   using Cfg = TsCfg<BN>;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(gemm_tc_ts_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    attr = true;
-  }
+  static unsigned long long attr = 0;
+  smem_optin(gemm_tc_ts_kernel<BN>, Cfg::SMEM_BYTES, attr);
   gemm_tc_ts_kernel<BN><<<pl->grid_ts, TC_THREADS, Cfg::SMEM_BYTES, st>>>(pl->tmA, pl->tmW3, pl->tmC, pl->tmC2, pl->tmR, pl->p);
   count_launch();
   return check_launch("gemm_tc_ts");
@@ -743,11 +740,8 @@ static int tc_launch_ts(const rstnet_tc_plan* pl, cudaStream_t st) {
 template <int BN, int PREC>
 static int tc_launch(const rstnet_tc_plan* pl, cudaStream_t st) {
   using Cfg = TcCfg<BN, PREC>;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(gemm_tc_kernel<BN, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    attr = true;
-  }
+  static unsigned long long attr = 0;
+  smem_optin(gemm_tc_kernel<BN, PREC>, Cfg::SMEM_BYTES, attr);
   gemm_tc_kernel<BN, PREC><<<pl->grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(pl->tmA, pl->tmW, pl->tmWlo, pl->p);
   count_launch();
   return check_launch("gemm_tc");

@@ -10,34 +10,58 @@ namespace rstnet {
 extern void count_launch();
 typedef __nv_bfloat16 bf16;
 
+// Sticky device-side error word (include/rstnet_b200.h: rstnet_device_error_flags): kernels cannot raise, so an
+// out-of-range id / position poisons its output and sets a bit the host reads at its next check.
+__device__ unsigned int g_lm_dev_err = 0;
+unsigned int lm_read_errors(bool clear) {
+  unsigned int v = 0;
+  cudaMemcpyFromSymbol(&v, g_lm_dev_err, sizeof(v));
+  if (clear && v) { const unsigned int z = 0; cudaMemcpyToSymbol(g_lm_dev_err, &z, sizeof(z)); }
+  return v;
+}
+
 __device__ __forceinline__ float b2f(bf16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ bf16 f2b(float v) { return __float2bfloat16(v); }
 
 // ---------------------------------------------------------------- embedding sum (llama_streaming.py:680-687)
 // x[b] = ((e_0 + e_1) + ... + e_{nq-1}) + wte[text]; every add rounds to bf16 as the eager bf16 model does;
 // id -1 contributes an exact zero row (ScaledEmbedding, :505-517).
+// nn.Embedding raises on ids outside the table; here such an id (anything but the zero token -1 below 0, or >= rows)
+// yields a NaN row and sets error bit 1.
 __global__ void embed_sum_kernel(const long long* __restrict__ seq, int seq_stride, const bf16* __restrict__ wte,
-                                 const bf16* const* __restrict__ tables, int n_q, int E, bf16* __restrict__ x) {
+                                 const bf16* const* __restrict__ tables, int n_q, int E, bf16* __restrict__ x,
+                                 long long wte_rows, long long table_rows) {
   const int b = blockIdx.x;
   const long long* ids = seq + (long long)b * seq_stride;
+  bool bad = ids[0] < -1 || ids[0] >= wte_rows;
+  for (int cb = 0; cb < n_q; ++cb) bad |= ids[cb + 1] < -1 || ids[cb + 1] >= table_rows;
+  if (bad && threadIdx.x == 0) atomicOr(&g_lm_dev_err, 1u);
   for (int d = threadIdx.x; d < E; d += blockDim.x) {
     float acc = 0.f;
-    for (int cb = 0; cb < n_q; ++cb) {
-      const long long id = ids[cb + 1];
-      const float e = id < 0 ? 0.f : b2f(tables[cb][id * E + d]);
-      acc = cb == 0 ? e : b2f(f2b(acc + e));
+    if (bad) {
+      acc = __int_as_float(0x7fc00000);
+    } else {
+      for (int cb = 0; cb < n_q; ++cb) {
+        const long long id = ids[cb + 1];
+        const float e = id < 0 ? 0.f : b2f(tables[cb][id * E + d]);
+        acc = cb == 0 ? e : b2f(f2b(acc + e));
+      }
+      const long long tid = ids[0];
+      acc = b2f(f2b(acc + (tid < 0 ? 0.f : b2f(wte[tid * E + d]))));
     }
-    acc = b2f(f2b(acc + b2f(wte[ids[0] * E + d])));
     x[(long long)b * E + d] = f2b(acc);
   }
 }
 
 // out[b] = table[id[b]] (zero row for id < 0): depth-transformer token embeddings (llama_streaming.py:738-742)
 __global__ void embed_rows_kernel(const long long* __restrict__ ids, int id_stride, const bf16* __restrict__ table, int D,
-                                  bf16* __restrict__ out) {
+                                  bf16* __restrict__ out, long long rows) {
   const int b = blockIdx.x;
   const long long id = ids[(long long)b * id_stride];
-  for (int d = threadIdx.x; d < D; d += blockDim.x) out[(long long)b * D + d] = id < 0 ? f2b(0.f) : table[id * D + d];
+  const bool bad = id < -1 || id >= rows;
+  if (bad && threadIdx.x == 0) atomicOr(&g_lm_dev_err, 1u);
+  for (int d = threadIdx.x; d < D; d += blockDim.x)
+    out[(long long)b * D + d] = bad ? f2b(__int_as_float(0x7fc00000)) : (id < 0 ? f2b(0.f) : table[id * D + d]);
 }
 
 // ---------------------------------------------------------------- RMSNorm, fp32 inside (lit_model.py:707-714;
@@ -68,63 +92,89 @@ __global__ void rms_norm_kernel(const bf16* __restrict__ x, const bf16* __restri
 }
 
 // ---------------------------------------------------------------- RoPE (rotate-half, bf16 cos/sin rows) + KV ring append
-// qkv [B][nh][3][hs] (litgpt per-group interleave, llama_streaming.py:957-963); writes rotated q to q_out [B][nh*hs],
-// rotated k and v into kv[2][B][nh][cap][hs] at slot (*offset % cap)  (lit_model.py:560-573, 620-634).
+// Rows are (time, stream) pairs, time-major: row r = tl * B + b holds stream b at position *offset + tl (a decode step is
+// tl == 0 for every row; a prefill chunk carries several consecutive positions per stream).
+// qkv [row][n_kv][q_per_kv + 2][hs] (litgpt per-group interleave, llama_streaming.py:952-963; MHA is q_per_kv == 1);
+// writes rotated q to q_out [row][n_head*hs] (head h = g*q_per_kv + j), rotated k and v into kv[2][B][n_kv][cap][hs] at
+// slot (pos % cap)  (lit_model.py:560-573, 620-634).  Only the first rope_n dims rotate (rotary_percentage < 1,
+// llama_streaming.py:979-982); the tables are [rope_rows][rope_n].  A position beyond the tables (the reference's
+// cos.index_select would raise) poisons q/k with NaN and sets error bit 2.
 __global__ void rope_kv_append_bf16_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ cosb, const bf16* __restrict__ sinb,
                                            const long long* __restrict__ offset, bf16* __restrict__ q_out, bf16* __restrict__ kv,
-                                           int B, int nh, int hs, int cap) {
-  const int b = blockIdx.x / nh, h = blockIdx.x % nh;
-  const long long pos = *offset;
+                                           int ostride, int B, int n_kv, int q_per_kv, int hs, int cap, int rope_n,
+                                           long long rope_rows) {
+  const int row = blockIdx.x / n_kv, g = blockIdx.x % n_kv;
+  const int b = row % B;
+  const long long pos = offset[(long long)b * ostride] + row / B;   // per-stream counters (ostride 1) or one shared (0)
   const int slot = (int)(pos % cap);
-  const bf16* base = qkv + ((long long)b * nh + h) * 3 * hs;
-  const bf16* c = cosb + pos * hs;
-  const bf16* s = sinb + pos * hs;
-  bf16* kdst = kv + (((long long)b * nh + h) * cap + slot) * hs;
-  bf16* vdst = kv + (long long)B * nh * cap * hs + (((long long)b * nh + h) * cap + slot) * hs;
-  const int half = hs / 2;
-  for (int d = threadIdx.x; d < hs; d += blockDim.x) {
-    const float cd = b2f(c[d]), sd = b2f(s[d]);
-    // roped = (x * cos) + (rotated * sin), each op rounded to bf16 as the eager bf16 model does
-    const float qx = b2f(base[d]), kx = b2f(base[hs + d]);
-    const float qr = d < half ? -b2f(base[d + half]) : b2f(base[d - half]);
-    const float kr = d < half ? -b2f(base[hs + d + half]) : b2f(base[hs + d - half]);
-    const float qv = b2f(f2b(b2f(f2b(qx * cd)) + b2f(f2b(qr * sd))));
-    const float kvv = b2f(f2b(b2f(f2b(kx * cd)) + b2f(f2b(kr * sd))));
-    q_out[((long long)b * nh + h) * hs + d] = f2b(qv);
-    kdst[d] = f2b(kvv);
-    vdst[d] = base[2 * hs + d];
+  const bool bad = pos >= rope_rows;
+  if (bad && threadIdx.x == 0) atomicOr(&g_lm_dev_err, 2u);
+  const bf16* base = qkv + ((long long)row * n_kv + g) * (q_per_kv + 2) * hs;
+  const bf16* c = cosb + (bad ? 0 : pos) * rope_n;
+  const bf16* s = sinb + (bad ? 0 : pos) * rope_n;
+  bf16* kdst = kv + (((long long)b * n_kv + g) * cap + slot) * hs;
+  bf16* vdst = kv + (long long)B * n_kv * cap * hs + (((long long)b * n_kv + g) * cap + slot) * hs;
+  const int half = rope_n / 2;
+  const bf16 nan = f2b(__int_as_float(0x7fc00000));
+  for (int i = threadIdx.x; i < (q_per_kv + 1) * hs; i += blockDim.x) {
+    const int j = i / hs, d = i % hs;           // j < q_per_kv: query j of the group; j == q_per_kv: the key
+    const bf16* x = base + (long long)j * hs;
+    bf16 o;
+    if (d < rope_n) {
+      // roped = (x * cos) + (rotated * sin), each op rounded to bf16 as the eager bf16 model does
+      const float cd = b2f(c[d]), sd = b2f(s[d]);
+      const float xv = b2f(x[d]);
+      const float xr = d < half ? -b2f(x[d + half]) : b2f(x[d - half]);
+      o = bad ? nan : f2b(b2f(f2b(xv * cd)) + b2f(f2b(xr * sd)));
+    } else {
+      o = x[d];
+    }
+    if (j < q_per_kv) q_out[((long long)row * n_kv * q_per_kv + (long long)g * q_per_kv + j) * hs + d] = o;
+    else kdst[d] = o;
   }
+  const bf16* vsrc = base + (long long)(q_per_kv + 1) * hs;
+  for (int d = threadIdx.x; d < hs; d += blockDim.x) vdst[d] = vsrc[d];
 }
 
-// ---------------------------------------------------------------- ring decode attention (T == 1)
-// one CTA per (head, stream); 8 lanes share a key row (16 dims = 32 bytes each, so a warp load covers 4 whole
-// 256-byte rows = 1 KB contiguous); per-group online softmax, combined across groups / warps at the end.
+// ---------------------------------------------------------------- ring decode attention (one query position per row)
+// one CTA per (G query heads sharing a kv head, row); 8 lanes share a key row (16 dims = 32 bytes each, so a warp load
+// covers 4 whole 256-byte rows = 1 KB contiguous); per-group online softmax, combined across groups / warps at the end.
 // Mask = RingKVCache.complete + (pos_k>=0)&(delta>=0)&(delta<context) (llama_streaming.py:983-992).
-template <int HS>
+// Row r = tl*B + b queries stream b at position *offset + tl; all positions of the launch are already in the ring
+// (the caller guarantees no slot a query still needs has been overwritten: see GPT.forward_global's prefill path).
+template <int HS, int G>
 __global__ void __launch_bounds__(256) ring_decode_attention_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kv,
                                                                     const long long* __restrict__ offset, bf16* __restrict__ out,
-                                                                    int B, int nh, int cap, int context, float scale) {
+                                                                    int ostride, int B, int nh, int n_kv, int cap, int context,
+                                                                    float scale) {
   constexpr int DPL = HS / 8;  // dims per lane
-  const int h = blockIdx.x, b = blockIdx.y;
+  const int h0 = blockIdx.x * G, row = blockIdx.y;
+  const int b = row % B;
+  const int g = h0 / (nh / n_kv);
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int grp = lane / 8, sub = lane % 8;
   const int nwarps = blockDim.x / 32;
-  const long long pos = *offset;  // position of the query; its key/value were appended just before
+  const long long pos = offset[(long long)b * ostride] + row / B;  // position of the query; its key/value were appended just before
   long long lo = pos - context + 1;
   if (lo < 0) lo = 0;
   if (lo < pos + 2 - cap) lo = pos + 2 - cap;  // ring quirk: the oldest slot is labelled end_offset and masked
   const long long nkeys = pos - lo + 1;
-  const bf16* Kb = kv + ((long long)b * nh + h) * cap * HS;
-  const bf16* Vb = Kb + (long long)B * nh * cap * HS;
-  float qf[DPL];
-  {
-    const bf16* qp = q + ((long long)b * nh + h) * HS + sub * DPL;
+  const bf16* Kb = kv + ((long long)b * n_kv + g) * cap * HS;
+  const bf16* Vb = Kb + (long long)B * n_kv * cap * HS;
+  float qf[G][DPL];
 #pragma unroll
-    for (int i = 0; i < DPL; ++i) qf[i] = b2f(qp[i]);
+  for (int u = 0; u < G; ++u) {
+    const bf16* qp = q + ((long long)row * nh + h0 + u) * HS + sub * DPL;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) qf[u][i] = b2f(qp[i]);
   }
-  float m = -INFINITY, l = 0.f, acc[DPL];
+  float m[G], l[G], acc[G][DPL];
 #pragma unroll
-  for (int i = 0; i < DPL; ++i) acc[i] = 0.f;
+  for (int u = 0; u < G; ++u) {
+    m[u] = -INFINITY; l[u] = 0.f;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) acc[u][i] = 0.f;
+  }
   // software pipeline: the K/V rows of the next iteration are in flight while this one is reduced
   uint4 kr[DPL / 8], vr[DPL / 8], kn[DPL / 8], vn[DPL / 8];
   auto load_rows = [&](long long j0, uint4* kd, uint4* vd) {
@@ -142,62 +192,79 @@ __global__ void __launch_bounds__(256) ring_decode_attention_kernel(const bf16* 
     const bool more = j0 + jstep < nkeys;
     if (more) load_rows(j0 + jstep, kn, vn);
     const bool valid = j0 + grp < nkeys;
-    float dot = 0.f;
+    float dot[G];
+#pragma unroll
+    for (int u = 0; u < G; ++u) dot[u] = 0.f;
 #pragma unroll
     for (int i = 0; i < DPL / 8; ++i) {
       const bf16* kk = reinterpret_cast<const bf16*>(&kr[i]);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) dot = fmaf(qf[i * 8 + e], b2f(kk[e]), dot);
-    }
-    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
-    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
-    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
-    if (valid) {
-      const float s = dot * scale;
-      const float m_new = fmaxf(m, s);
-      const float corr = __expf(m - m_new), pj = __expf(s - m_new);
-      l = l * corr + pj;
+      for (int e = 0; e < 8; ++e) {
+        const float kf = b2f(kk[e]);
 #pragma unroll
-      for (int i = 0; i < DPL / 8; ++i) {
-        const bf16* vv = reinterpret_cast<const bf16*>(&vr[i]);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[i * 8 + e] = fmaf(pj, b2f(vv[e]), acc[i * 8 + e] * corr);
+        for (int u = 0; u < G; ++u) dot[u] = fmaf(qf[u][i * 8 + e], kf, dot[u]);
       }
-      m = m_new;
+    }
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], 1);
+      dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], 2);
+      dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], 4);
+    }
+    if (valid) {
+#pragma unroll
+      for (int u = 0; u < G; ++u) {
+        const float s = dot[u] * scale;
+        const float m_new = fmaxf(m[u], s);
+        const float corr = __expf(m[u] - m_new), pj = __expf(s - m_new);
+        l[u] = l[u] * corr + pj;
+#pragma unroll
+        for (int i = 0; i < DPL / 8; ++i) {
+          const bf16* vv = reinterpret_cast<const bf16*>(&vr[i]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[u][i * 8 + e] = fmaf(pj, b2f(vv[e]), acc[u][i * 8 + e] * corr);
+        }
+        m[u] = m_new;
+      }
     }
     if (more) {
 #pragma unroll
       for (int i = 0; i < DPL / 8; ++i) { kr[i] = kn[i]; vr[i] = vn[i]; }
     }
   }
-  // combine the 4 key groups of the warp (lanes sub, sub+8, sub+16, sub+24 hold the same dims)
+  __shared__ float sm_m[G][8], sm_l[G][8], sm_acc[G][8][HS];
 #pragma unroll
-  for (int o = 8; o <= 16; o <<= 1) {
-    const float mo = __shfl_xor_sync(0xffffffffu, m, o), lo_ = __shfl_xor_sync(0xffffffffu, l, o);
-    const float mn = fmaxf(m, mo);
-    const float ca = mn == -INFINITY ? 0.f : __expf(m - mn), cb = mn == -INFINITY ? 0.f : __expf(mo - mn);
-    l = l * ca + lo_ * cb;
+  for (int u = 0; u < G; ++u) {
+    // combine the 4 key groups of the warp (lanes sub, sub+8, sub+16, sub+24 hold the same dims)
+    float mu = m[u], lu = l[u];
 #pragma unroll
-    for (int i = 0; i < DPL; ++i) acc[i] = acc[i] * ca + __shfl_xor_sync(0xffffffffu, acc[i], o) * cb;
-    m = mn;
-  }
-  __shared__ float sm_m[8], sm_l[8], sm_acc[8][HS];
-  if (grp == 0) {
-    if (sub == 0) { sm_m[warp] = m; sm_l[warp] = l; }
+    for (int o = 8; o <= 16; o <<= 1) {
+      const float mo = __shfl_xor_sync(0xffffffffu, mu, o), lo_ = __shfl_xor_sync(0xffffffffu, lu, o);
+      const float mn = fmaxf(mu, mo);
+      const float ca = mn == -INFINITY ? 0.f : __expf(mu - mn), cb = mn == -INFINITY ? 0.f : __expf(mo - mn);
+      lu = lu * ca + lo_ * cb;
 #pragma unroll
-    for (int i = 0; i < DPL; ++i) sm_acc[warp][sub * DPL + i] = acc[i];
+      for (int i = 0; i < DPL; ++i) acc[u][i] = acc[u][i] * ca + __shfl_xor_sync(0xffffffffu, acc[u][i], o) * cb;
+      mu = mn;
+    }
+    if (grp == 0) {
+      if (sub == 0) { sm_m[u][warp] = mu; sm_l[u][warp] = lu; }
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) sm_acc[u][warp][sub * DPL + i] = acc[u][i];
+    }
   }
   __syncthreads();
-  for (int d = threadIdx.x; d < HS; d += blockDim.x) {
+  for (int idx = threadIdx.x; idx < G * HS; idx += blockDim.x) {
+    const int u = idx / HS, d = idx % HS;
     float mm = -INFINITY;
-    for (int w = 0; w < nwarps; ++w) mm = fmaxf(mm, sm_m[w]);
+    for (int w = 0; w < nwarps; ++w) mm = fmaxf(mm, sm_m[u][w]);
     float ll = 0.f, a = 0.f;
     for (int w = 0; w < nwarps; ++w) {
-      const float c = sm_m[w] == -INFINITY ? 0.f : __expf(sm_m[w] - mm);
-      ll += sm_l[w] * c;
-      a += sm_acc[w][d] * c;
+      const float c = sm_m[u][w] == -INFINITY ? 0.f : __expf(sm_m[u][w] - mm);
+      ll += sm_l[u][w] * c;
+      a += sm_acc[u][w][d] * c;
     }
-    out[((long long)b * nh + h) * HS + d] = f2b(a / ll);
+    out[((long long)row * nh + h0 + u) * HS + d] = f2b(a / ll);
   }
 }
 
@@ -215,9 +282,10 @@ __global__ void silu_mul_kernel(const bf16* __restrict__ ab, bf16* __restrict__ 
 
 // ---------------------------------------------------------------- depth-transformer attention (<= 8 keys, no RoPE)
 // qkv [B][3][H][hd] ((p h d) layout, transformer.py:391-393); kvd [2][B][H][cap][hd]; step k: append at slot k,
-// attend keys 0..k (cap == dep_q so the ring never wraps inside a frame).
+// attend keys 0..k (cap == dep_q so the ring never wraps inside a frame).  ring_quirk != 0: the streaming form
+// (forward_codecformer); 0: the non-streaming form (forward_local: KVCacheResult.from_kv keeps every key).
 __global__ void depth_attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kvd, bf16* __restrict__ out, int B, int H,
-                                       int hd, int cap, int step) {
+                                       int hd, int cap, int step, int ring_quirk) {
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int lane = threadIdx.x;
   const int HD = H * hd;
@@ -234,7 +302,7 @@ __global__ void depth_attention_kernel(const bf16* __restrict__ qkv, bf16* __res
   float mx = -INFINITY;
   // RingKVCache.complete labels slot end_offset % capacity with position end_offset (modules/transformer.py:258-263),
   // so on the last codebook step (end_offset == capacity) key 0 is masked by `delta >= 0`.
-  const int j_lo = step + 2 - cap > 0 ? step + 2 - cap : 0;
+  const int j_lo = (ring_quirk && step + 2 - cap > 0) ? step + 2 - cap : 0;
   for (int j = j_lo; j <= step; ++j) {
     float dot = 0.f;
     for (int d = lane; d < hd; d += 32) dot = fmaf(b2f(qp[d]), b2f(Kb[(long long)j * hd + d]), dot);
@@ -274,6 +342,43 @@ __device__ __forceinline__ uint32_t bf16_order_key(bf16 v) {
   return (u & 0x8000u) ? (~u & 0xFFFFu) : (u | 0x8000u);
 }
 
+// block-wide argmax in the order (value desc, index asc); every thread returns the winner
+__device__ __forceinline__ void block_argmax(float& bv, int& bi, float* s_val, int* s_idx) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  __syncthreads();   // the previous round's readers are done with s_val / s_idx
+  if (tid % 32 == 0) { s_val[tid / 32] = bv; s_idx[tid / 32] = bi; }
+  __syncthreads();
+  if (tid < 32) {
+    bv = tid < nthr / 32 ? s_val[tid] : -INFINITY;
+    bi = tid < nthr / 32 ? s_idx[tid] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (tid == 0) { s_val[0] = bv; s_idx[0] = bi; }
+  }
+  __syncthreads();
+  bv = s_val[0];
+  bi = s_idx[0];
+}
+
+__device__ __forceinline__ float gumbel_of(uint32_t seed, uint32_t stepc, uint32_t row, uint32_t id) {
+  const uint32_t u = hash_u32(seed, stepc, row, id);
+  const float uni = ((float)(u >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
+  return -logf(-logf(uni));   // argmax_i (l_i/temp + G_i)  ==  argmax_i softmax(l/temp)_i / Exp(1)_i
+}
+
+// top_k == 0: argmax.  1..64: ordered selection of the top-k (below), noise keyed by rank.  65..SAMPLE_CAND: threshold
+// select (the k largest by (value desc, index asc), found with the histogram + candidate list), noise keyed by token id.
+// top_k < 0: multinomial over all n_valid ids (sample_token with top_k == 0, utils/sampling.py:97-101).
 __global__ void sample_kernel(const bf16* __restrict__ logits, int V, int n_valid, int top_k, float temp, uint32_t seed,
                               const long long* __restrict__ step_counter, long long* __restrict__ tokens, int tok_stride) {
   __shared__ float s_val[32];
@@ -283,15 +388,30 @@ __global__ void sample_kernel(const bf16* __restrict__ logits, int V, int n_vali
   __shared__ int hist[SAMPLE_HISTS][256];
   __shared__ float cand_v[SAMPLE_CAND];
   __shared__ int cand_i[SAMPLE_CAND];
-  __shared__ int s_sel[4];   // [0] high-byte bin, [1] count above it, [2] threshold key, [3] candidate count
+  __shared__ int s_sel[5];   // [0] high-byte bin, [1] count above the threshold key, [2] threshold key, [3] candidate count, [4] ties taken
   const int row = blockIdx.x;
   const bf16* lr = logits + (long long)row * V;
-  const int kk = top_k <= 0 ? 1 : (top_k > 64 ? 64 : top_k);
   const int tid = threadIdx.x, nthr = blockDim.x;
+  const uint32_t stepc = step_counter ? (uint32_t)(*step_counter) : 0u;
 
+  if (top_k < 0) {   // full multinomial
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    const float inv_t = 1.0f / temp;
+    for (int i = tid; i < n_valid; i += nthr) {
+      const float sc = b2f(lr[i]) * inv_t + gumbel_of(seed, stepc, (uint32_t)row, (uint32_t)i);
+      if (sc > bv) { bv = sc; bi = i; }
+    }
+    block_argmax(bv, bi, s_val, s_idx);
+    if (tid == 0) tokens[(long long)row * tok_stride] = bi;
+    return;
+  }
+
+  const bool big = top_k > 64;
+  const int kk = top_k <= 0 ? 1 : (big ? top_k : top_k);
   int n_items = n_valid;
   bool from_list = false;
-  if (kk > 1 && n_valid > 4 * SAMPLE_CAND) {
+  if (big || (kk > 1 && n_valid > 4 * SAMPLE_CAND)) {
     int* myh = hist[(tid / 32) % SAMPLE_HISTS];
     for (int pass = 0; pass < 2; ++pass) {
       for (int i = tid; i < SAMPLE_HISTS * 256; i += nthr) (&hist[0][0])[i] = 0;
@@ -314,7 +434,7 @@ __global__ void sample_kernel(const bf16* __restrict__ logits, int V, int n_vali
         int above = pass ? s_sel[1] : 0, b = 255;
         while (b > 0 && above + hist[0][b] < kk) { above += hist[0][b]; --b; }
         if (pass == 0) { s_sel[0] = b; s_sel[1] = above; }
-        else { s_sel[2] = (s_sel[0] << 8) | b; s_sel[3] = 0; }
+        else { s_sel[2] = (s_sel[0] << 8) | b; s_sel[1] = above; s_sel[3] = 0; s_sel[4] = 0; }
       }
       __syncthreads();
     }
@@ -327,7 +447,57 @@ __global__ void sample_kernel(const bf16* __restrict__ logits, int V, int n_vali
       }
     }
     __syncthreads();
-    if (s_sel[3] <= SAMPLE_CAND) { from_list = true; n_items = s_sel[3]; }   // else: massive ties, scan the row
+    if (s_sel[3] <= SAMPLE_CAND) { from_list = true; n_items = s_sel[3]; }   // else: massive ties at the threshold
+  }
+
+  if (big) {
+    const uint32_t thr = (uint32_t)s_sel[2];
+    const int above = s_sel[1];
+    const int need = kk - above;          // ties at the threshold to take, lowest ids first
+    const float inv_t = 1.0f / temp;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    if (from_list) {
+      for (int t = tid; t < n_items; t += nthr) {
+        const float v = cand_v[t];
+        const int id = cand_i[t];
+        bool in = bf16_order_key(f2b(v)) > thr;
+        if (!in) {
+          int rank = 0;
+          for (int j = 0; j < n_items; ++j) rank += (cand_v[j] == v && cand_i[j] < id) ? 1 : 0;
+          in = rank < need;
+        }
+        if (in) {
+          const float sc = v * inv_t + gumbel_of(seed, stepc, (uint32_t)row, (uint32_t)id);
+          if (sc > bv || (sc == bv && id < bi)) { bv = sc; bi = id; }
+        }
+      }
+    } else {
+      // more than SAMPLE_CAND logits share the threshold value: walk the row in index order, counting ties
+      for (int base = 0; base < n_valid; base += nthr) {
+        const int i = base + tid;
+        const uint32_t k = i < n_valid ? bf16_order_key(lr[i]) : 0u;
+        const bool tie = i < n_valid && k == thr;
+        const unsigned bal = __ballot_sync(0xffffffffu, tie);
+        const int wpre = __popc(bal & ((1u << (tid % 32)) - 1u));
+        __syncthreads();
+        if (tid % 32 == 0) s_idx[tid / 32] = __popc(bal);
+        __syncthreads();
+        int before = s_sel[4];
+        for (int w = 0; w < tid / 32; ++w) before += s_idx[w];
+        const bool in = i < n_valid && (k > thr || (tie && before + wpre < need));
+        if (in) {
+          const float sc = b2f(lr[i]) * inv_t + gumbel_of(seed, stepc, (uint32_t)row, (uint32_t)i);
+          if (sc > bv || (sc == bv && i < bi)) { bv = sc; bi = i; }
+        }
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int w = 0; w < nthr / 32; ++w) t += s_idx[w]; s_sel[4] += t; }
+        __syncthreads();
+      }
+    }
+    block_argmax(bv, bi, s_val, s_idx);
+    if (tid == 0) tokens[(long long)row * tok_stride] = bi;
+    return;
   }
 
   float last_v = INFINITY;
@@ -342,33 +512,14 @@ __global__ void sample_kernel(const bf16* __restrict__ logits, int V, int n_vali
       const bool after = v < last_v || (v == last_v && id > last_i);
       if (after && (v > bv || (v == bv && id < bi))) { bv = v; bi = id; }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-    }
-    if (tid % 32 == 0) { s_val[tid / 32] = bv; s_idx[tid / 32] = bi; }
-    __syncthreads();
-    if (tid < 32) {
-      bv = tid < nthr / 32 ? s_val[tid] : -INFINITY;
-      bi = tid < nthr / 32 ? s_idx[tid] : 0x7fffffff;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-      }
-      if (tid == 0) { top_v[r] = bv; top_i[r] = bi; }
-    }
-    __syncthreads();
-    last_v = top_v[r];
-    last_i = top_i[r];
+    block_argmax(bv, bi, s_val, s_idx);
+    if (tid == 0) { top_v[r] = bv; top_i[r] = bi; }
+    last_v = bv;
+    last_i = bi;
   }
   if (tid == 0) {
     int pick = top_i[0];
     if (top_k > 0) {
-      const uint32_t stepc = step_counter ? (uint32_t)(*step_counter) : 0u;
       float best = -INFINITY;
       for (int r = 0; r < kk; ++r) {
         const float w = expf((top_v[r] - top_v[0]) / temp);
@@ -386,19 +537,21 @@ __global__ void sample_kernel(const bf16* __restrict__ logits, int V, int n_vali
 }  // namespace rstnet
 using namespace rstnet;
 
-extern "C" int rstnet_lm_embed_sum_bf16(const int64_t* seq, int32_t seq_stride, const void* wte, const void* const* tables_dev,
-                                        int32_t n_q, int32_t E, void* x, int32_t B, rstnet_stream_t stream) {
-  RSTNET_REQUIRE(seq && wte && tables_dev && x && B > 0, "lm_embed_sum: bad argument");
-  embed_sum_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((const long long*)seq, seq_stride, (const bf16*)wte,
-                                                        (const bf16* const*)tables_dev, n_q, E, (bf16*)x);
+extern "C" int rstnet_lm_embed_sum_bf16(const int64_t* seq, int32_t seq_stride, const void* wte, int64_t wte_rows,
+                                        const void* const* tables_dev, int64_t table_rows, int32_t n_q, int32_t E, void* x,
+                                        int32_t rows, rstnet_stream_t stream) {
+  RSTNET_REQUIRE(seq && wte && tables_dev && x && rows > 0 && wte_rows > 0 && table_rows > 0, "lm_embed_sum: bad argument");
+  embed_sum_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>((const long long*)seq, seq_stride, (const bf16*)wte,
+                                                           (const bf16* const*)tables_dev, n_q, E, (bf16*)x, wte_rows, table_rows);
   count_launch();
   return check_launch("lm_embed_sum");
 }
 
-extern "C" int rstnet_lm_embed_rows_bf16(const int64_t* ids, int32_t id_stride, const void* table, int32_t D, void* out, int32_t B,
-                                         rstnet_stream_t stream) {
-  RSTNET_REQUIRE(ids && table && out && B > 0, "lm_embed_rows: bad argument");
-  embed_rows_kernel<<<B, 128, 0, (cudaStream_t)stream>>>((const long long*)ids, id_stride, (const bf16*)table, D, (bf16*)out);
+extern "C" int rstnet_lm_embed_rows_bf16(const int64_t* ids, int32_t id_stride, const void* table, int64_t table_rows, int32_t D,
+                                         void* out, int32_t rows, rstnet_stream_t stream) {
+  RSTNET_REQUIRE(ids && table && out && rows > 0 && table_rows > 0, "lm_embed_rows: bad argument");
+  embed_rows_kernel<<<rows, 128, 0, (cudaStream_t)stream>>>((const long long*)ids, id_stride, (const bf16*)table, D, (bf16*)out,
+                                                            table_rows);
   count_launch();
   return check_launch("lm_embed_rows");
 }
@@ -411,28 +564,40 @@ extern "C" int rstnet_lm_rms_norm_bf16(const void* x, const void* w, void* y, in
   return check_launch("lm_rms_norm");
 }
 
-extern "C" int rstnet_lm_rope_kv_append_bf16(const void* qkv, const void* cos_tab, const void* sin_tab, const int64_t* offset,
-                                             void* q_out, void* kv, int32_t B, int32_t nh, int32_t hs, int32_t cap,
+extern "C" int rstnet_lm_rope_kv_append_bf16(const void* qkv, const void* cos_tab, const void* sin_tab, int64_t rope_rows,
+                                             int32_t rope_n, const int64_t* offset, int32_t offset_stride, void* q_out, void* kv,
+                                             int32_t rows, int32_t B, int32_t n_head, int32_t n_kv, int32_t hs, int32_t cap,
                                              rstnet_stream_t stream) {
   RSTNET_REQUIRE(qkv && cos_tab && sin_tab && offset && q_out && kv, "lm_rope_kv_append: null pointer");
-  rope_kv_append_bf16_kernel<<<B * nh, 64, 0, (cudaStream_t)stream>>>((const bf16*)qkv, (const bf16*)cos_tab, (const bf16*)sin_tab,
-                                                                      (const long long*)offset, (bf16*)q_out, (bf16*)kv, B, nh, hs, cap);
+  RSTNET_REQUIRE(rows > 0 && B > 0 && rows % B == 0, "lm_rope_kv_append: rows (%d) must be a multiple of the stream count (%d)", rows, B);
+  RSTNET_REQUIRE(n_kv > 0 && n_head % n_kv == 0, "lm_rope_kv_append: n_head (%d) must be a multiple of n_kv (%d)", n_head, n_kv);
+  RSTNET_REQUIRE(rope_n >= 0 && rope_n <= hs && rope_n % 2 == 0 && rope_rows > 0, "lm_rope_kv_append: bad rope table (%d of %d dims)", rope_n, hs);
+  rope_kv_append_bf16_kernel<<<rows * n_kv, 64, 0, (cudaStream_t)stream>>>((const bf16*)qkv, (const bf16*)cos_tab, (const bf16*)sin_tab,
+                                                                           (const long long*)offset, (bf16*)q_out, (bf16*)kv,
+                                                                           offset_stride ? 1 : 0, B, n_kv, n_head / n_kv, hs, cap,
+                                                                           rope_n, rope_rows);
   count_launch();
   return check_launch("lm_rope_kv_append");
 }
 
-extern "C" int rstnet_lm_ring_decode_attention_bf16(const void* q, const void* kv, const int64_t* offset, void* out, int32_t B,
-                                                    int32_t nh, int32_t hs, int32_t cap, int32_t context, rstnet_stream_t stream) {
+extern "C" int rstnet_lm_ring_decode_attention_bf16(const void* q, const void* kv, const int64_t* offset, int32_t offset_stride,
+                                                    void* out, int32_t rows, int32_t B, int32_t n_head, int32_t n_kv, int32_t hs,
+                                                    int32_t cap, int32_t context, rstnet_stream_t stream) {
   RSTNET_REQUIRE(q && kv && offset && out, "lm_ring_decode_attention: null pointer");
   RSTNET_REQUIRE(hs == 128 || hs == 64, "lm_ring_decode_attention: head_size must be 64 or 128 (got %d)", hs);
+  RSTNET_REQUIRE(rows > 0 && B > 0 && rows % B == 0, "lm_ring_decode_attention: rows (%d) must be a multiple of the stream count (%d)", rows, B);
+  RSTNET_REQUIRE(n_kv > 0 && n_head % n_kv == 0, "lm_ring_decode_attention: n_head (%d) must be a multiple of n_kv (%d)", n_head, n_kv);
   const float scale = 1.0f / sqrtf((float)hs);
-  dim3 grid(nh, B);
-  if (hs == 128)
-    ring_decode_attention_kernel<128><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)q, (const bf16*)kv, (const long long*)offset,
-                                                                               (bf16*)out, B, nh, cap, context, scale);
-  else
-    ring_decode_attention_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)q, (const bf16*)kv, (const long long*)offset,
-                                                                              (bf16*)out, B, nh, cap, context, scale);
+  const int q_per_kv = n_head / n_kv;
+  const int G = q_per_kv % 2 == 0 ? 2 : 1;   // query heads per CTA sharing the K/V rows (the rest of a group hits L2)
+  dim3 grid(n_head / G, rows);
+  cudaStream_t st = (cudaStream_t)stream;
+#define RSTNET_ATTN(HS_, G_)                                                                                               \
+  ring_decode_attention_kernel<HS_, G_><<<grid, 256, 0, st>>>((const bf16*)q, (const bf16*)kv, (const long long*)offset, \
+                                                               (bf16*)out, offset_stride ? 1 : 0, B, n_head, n_kv, cap, context, scale)
+  if (hs == 128) { if (G == 2) RSTNET_ATTN(128, 2); else RSTNET_ATTN(128, 1); }
+  else           { if (G == 2) RSTNET_ATTN(64, 2); else RSTNET_ATTN(64, 1); }
+#undef RSTNET_ATTN
   count_launch();
   return check_launch("lm_ring_decode_attention");
 }
@@ -448,10 +613,10 @@ extern "C" int rstnet_lm_silu_mul_bf16(const void* ab, void* out, int32_t M, int
 }
 
 extern "C" int rstnet_lm_depth_attention_bf16(const void* qkv, void* kvd, void* out, int32_t B, int32_t H, int32_t hd, int32_t cap,
-                                              int32_t step, rstnet_stream_t stream) {
+                                              int32_t step, int32_t ring_quirk, rstnet_stream_t stream) {
   RSTNET_REQUIRE(qkv && kvd && out, "lm_depth_attention: null pointer");
   RSTNET_REQUIRE(step >= 0 && step < cap && cap <= 8, "lm_depth_attention: step %d / capacity %d (<= 8) out of range", step, cap);
-  depth_attention_kernel<<<B * H, 32, 0, (cudaStream_t)stream>>>((const bf16*)qkv, (bf16*)kvd, (bf16*)out, B, H, hd, cap, step);
+  depth_attention_kernel<<<B * H, 32, 0, (cudaStream_t)stream>>>((const bf16*)qkv, (bf16*)kvd, (bf16*)out, B, H, hd, cap, step, ring_quirk);
   count_launch();
   return check_launch("lm_depth_attention");
 }
@@ -460,8 +625,9 @@ extern "C" int rstnet_lm_sample_bf16(const void* logits, int32_t rows, int32_t V
                                      uint32_t seed, const int64_t* step_counter, int64_t* tokens, int32_t tok_stride,
                                      rstnet_stream_t stream) {
   RSTNET_REQUIRE(logits && tokens && rows > 0 && V > 0, "lm_sample: bad argument");
-  RSTNET_REQUIRE(top_k <= 64 && (top_k <= 0 || temp > 0.f), "lm_sample: top_k <= 64 and temp > 0 required");
+  RSTNET_REQUIRE(top_k <= SAMPLE_CAND && (top_k == 0 || temp > 0.f), "lm_sample: top_k <= %d and temp > 0 required (top_k=%d)", SAMPLE_CAND, top_k);
   if (n_valid <= 0 || n_valid > V) n_valid = V;
+  if (top_k > n_valid) top_k = n_valid;   // torch.topk would raise; the whole support is the natural reading
   sample_kernel<<<rows, 1024, 0, (cudaStream_t)stream>>>((const bf16*)logits, V, n_valid, top_k, temp, seed,
                                                          (const long long*)step_counter, (long long*)tokens, tok_stride);
   count_launch();

@@ -212,6 +212,16 @@ __global__ void rvq_finish_kernel(const float* __restrict__ pval, const int* __r
   codes[(b * n_q + level) * T + t] = idx;
 }
 
+// Sticky device-side error word (rstnet_device_error_flags): F.embedding raises on a code outside [0, bins); here the
+// code is clamped (no out-of-bounds read) and bit 1 is set.
+__device__ unsigned int g_rvq_dev_err = 0;
+unsigned int rvq_read_errors(bool clear) {
+  unsigned int v = 0;
+  cudaMemcpyFromSymbol(&v, g_rvq_dev_err, sizeof(v));
+  if (clear && v) { const unsigned int z = 0; cudaMemcpyToSymbol(g_rvq_dev_err, &z, sizeof(z)); }
+  return v;
+}
+
 // decode: q[n][0:dim) = sum_{l<ns} E_l[c_l];  q[n][dim:2dim) = sum_{l>=ns} E_l[c_l]  (level order)
 __global__ void rvq_gather_kernel(const long long* __restrict__ codes, const float* __restrict__ E, float* __restrict__ q,
                                   long long N, int T, int n_q, int ns, int dim, int bins, int time_major) {
@@ -225,7 +235,10 @@ __global__ void rvq_gather_kernel(const long long* __restrict__ codes, const flo
     float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
     for (int l = 0; l < n_q; ++l) {
       long long c = codes[(b * n_q + l) * T + t];
-      c = c < 0 ? 0 : (c >= bins ? bins - 1 : c);
+      if (c < 0 || c >= bins) {
+        if (d4 == 0) atomicOr(&g_rvq_dev_err, 1u);
+        c = c < 0 ? 0 : bins - 1;
+      }
       const float4 e = *reinterpret_cast<const float4*>(E + ((long long)l * bins + c) * dim + 4 * d4);
       if (l < ns) { s1.x += e.x; s1.y += e.y; s1.z += e.z; s1.w += e.w; }
       else        { s2.x += e.x; s2.y += e.y; s2.z += e.z; s2.w += e.w; }
@@ -258,8 +271,8 @@ extern "C" int rstnet_rvq_encode_f32(const float* x, int64_t ldx, const float* E
   RSTNET_REQUIRE(dim % 16 == 0 && bins % RQ_BN == 0 && ldx % 4 == 0, "rvq_encode: dim %% 16, bins %% 128, ldx %% 4 required");
   const size_t smem = rvq_smem_bytes(dim);
   RSTNET_REQUIRE(smem <= 220 * 1024, "rvq_encode: dim too large for shared memory");
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(rvq_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); attr = true; }
+  static unsigned long long attr = 0;
+  smem_optin(rvq_level_kernel, 220 * 1024, attr);
   cudaStream_t st = (cudaStream_t)stream;
   const int nch = bins / RQ_BN;
   char* w = (char*)work;

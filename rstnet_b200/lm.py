@@ -1,13 +1,18 @@
-"""B200-native streaming decode step of the speech-text LM behind the reference's Python API.
+"""B200-native decode path of the speech-text LM behind the reference's Python API.
 
-Mirrors ``models.llama_streaming.GPT`` (MLLM_v2/models/llama_streaming.py:520-766) for the streaming
-path (`with gpt.streaming(B):`, one frame = one position per call):
-  * ``forward_global(seq[B,9,1]) -> (transformer_out[B,1,E], text_logits[B,1,V])``  (:665-692)
-  * ``with gpt.codecformer.streaming(B): forward_codecformer(k, prev[B,1,1], transformer_out)`` (:727-749)
-  * ``_get_initial_token``, ``codecformer_text_emb``, token-id properties, identical state_dict keys
-    (LoRA merged / r == 0: ``...attn.attn.linear.weight`` etc., so reference checkpoints load).
-plus ``forward_step`` -- the whole frame (temporal step, text sampling, 8 depth steps with sampling) as
-one CUDA-graph replay; BASELINE.json names it although no such symbol exists upstream.
+Mirrors ``models.llama_streaming.GPT`` (MLLM_v2/models/llama_streaming.py:520-766):
+  * streaming (`with gpt.streaming(B):`): ``forward_global(seq[B,9,T]) -> (transformer_out[B,T,E], text_logits[B,T,V])``
+    (:665-692) -- T == 1 is the decode step, T > 1 a prefill chunk (T consecutive positions per stream, the KV ring
+    written in one pass; equal to T single-step calls);
+  * ``with gpt.codecformer.streaming(B): forward_codecformer(k, prev[B,1,1], transformer_out)`` (:727-749);
+  * outside a streaming scope ``forward_global`` is the reference's non-streaming form (positions 0..T-1, nothing kept) and
+    ``forward_local(local_start_token, sequence, transformer_out) -> logits[B,T,8,card]`` (:694-725) the teacher-forced
+    depth transformer -- the two calls `infer_no_streaming.py:232-308` makes;
+  * ``_get_initial_token``, ``codecformer_text_emb``, token-id properties, identical state_dict keys (LoRA keys
+    ``...lora_A / lora_B`` are merged into the base weights on load, :113-143, 368-406, 1120-1124);
+  * MHA and GQA (``n_query_groups``), partial rotary (``rotary_percentage``), Llama-3.1 ``rope_adjustments``;
+plus ``forward_step`` -- the whole frame (temporal step, text sampling, 8 depth steps with sampling) as one CUDA-graph
+replay; BASELINE.json names it although no such symbol exists upstream.
 
 All arithmetic runs in librstnet_b200.so: tcgen05 weight-streaming GEMMs, ring decode attention, fused
 norm / RoPE / gating / sampling kernels.  bf16 weights and activations, fp32 accumulation, exactly the
@@ -20,12 +25,15 @@ from contextlib import contextmanager
 from dataclasses import dataclass
 from typing import Dict, Optional
 
+import numpy as np
 import torch
 from torch import nn
 
 from . import _lib, ops
 from ._lib import RstnetError
-from .codec import _register
+from .codec import _register, on_own_device
+
+MAX_ROWS = 128   # rows (stream, position) pairs per GEMM launch: the N operand of the weight-streaming GEMM
 
 
 @dataclass
@@ -41,6 +49,8 @@ class Config:
     norm_eps: float = 1e-5
     rope_base: int = 10000
     rotary_percentage: float = 1.0
+    rope_condense_ratio: int = 1
+    rope_adjustments: Optional[dict] = None
     padded_vocab_size: int = 152064
     audio_card: int = 2048
     n_q: int = 9
@@ -50,12 +60,28 @@ class Config:
     codecformer_layers: int = 6
     codecformer_dim_feedforward: int = 1024
     context: int = 3000
+    # LoRA (llama_streaming.py:447-470): only used to merge lora_A / lora_B found in a checkpoint
+    lora_r: int = 0
+    lora_alpha: int = 1
+    lora_dropout: float = 0.0
+    lora_query: bool = False
+    lora_key: bool = False
+    lora_value: bool = False
+    lora_projection: bool = False
+    lora_mlp: bool = False
+    lora_head: bool = False
 
     def __post_init__(self):
         if self.head_size is None:
             self.head_size = self.n_embd // self.n_head
         if self.n_query_groups is None:
             self.n_query_groups = self.n_head
+        if self.n_head % self.n_query_groups != 0:
+            raise ValueError("n_head must be a multiple of n_query_groups")
+
+    @property
+    def rope_n_elem(self) -> int:   # config.py:113
+        return int(self.rotary_percentage * self.head_size)
 
     @property
     def ff_hidden(self) -> int:  # modules/gating.py:40-43
@@ -120,16 +146,45 @@ class _DepthScope:
             st.depth_step = None
 
 
+# --------------------------------------------------------------------------------------- LoRA merge (host, once)
+def _lora_delta_qkv(A: torch.Tensor, B: torch.Tensor, c: Config, scaling: float, out_features: int) -> torch.Tensor:
+    """LoRAQKVLinear.get_lora_AB (llama_streaming.py:368-380 with conv1d :330-366 and zero_pad :255-328): one rank-r
+    update per enabled part of (q, k, v); the parts' rows are scattered to the per-group interleaved layout."""
+    enable = (c.lora_query, c.lora_key, c.lora_value)
+    n_en = sum(enable)
+    r = A.shape[0] // n_en
+    hs, nh, nkv = c.head_size, c.n_head, c.n_query_groups
+    shapes = [s for s, e in zip((hs * nh, hs * nkv, hs * nkv), enable) if e]
+    parts = [Bp @ Ap for Ap, Bp in zip(A.split(r, dim=0), B.split(shapes, dim=0))]
+    lora = torch.cat(parts, dim=0) * scaling                                        # [sum(shapes), in]
+    group = nh // nkv + 2
+    rows = torch.arange(out_features)
+    slot = (rows // hs) % group
+    ind = []
+    if enable[0]:
+        ind.append(rows[slot < group - 2])
+    if enable[1]:
+        ind.append(rows[slot == group - 2])
+    if enable[2]:
+        ind.append(rows[slot == group - 1])
+    ind = torch.cat(ind)
+    delta = lora.new_zeros(out_features, lora.shape[1])
+    delta.index_copy_(0, ind.to(lora.device), lora)
+    return delta
+
+
+def merge_lora_weights(model: "GPT") -> None:
+    """llama_streaming.merge_lora_weights (:1120-1124).  LoRA factors are merged when a checkpoint is loaded, so a GPT
+    here is always in the merged state; kept for call-site compatibility."""
+    return None
+
+
 class GPT(nn.Module):
     def __init__(self, config: Config, device=None, dtype=None):
         """device/dtype: create the (random-init) parameters directly there (a 7B model in bf16 on the GPU
         without a 28 GB fp32 host copy); default = CPU fp32 like the reference constructor."""
         super().__init__()
         c = self.config = config
-        if c.n_query_groups != c.n_head:
-            raise NotImplementedError("grouped-query configurations are not implemented yet (the 7B backbone is MHA)")
-        if c.rotary_percentage != 1.0:
-            raise NotImplementedError("partial rotary embeddings are not implemented")
         E, V, I, D, H = c.n_embd, c.padded_vocab_size, c.intermediate_size, c.codecformer_dim, c.ff_hidden
         g = torch.Generator(device=device if device is not None else "cpu").manual_seed(0)
         fk = dict(device=device, dtype=dtype)
@@ -145,7 +200,7 @@ class GPT(nn.Module):
         for l in range(c.n_layer):
             p = f"transformer.h.{l}"
             _register(self, f"{p}.norm_1.weight", ones(E))
-            _register(self, f"{p}.attn.attn.linear.weight", w_(3 * c.n_head * c.head_size, E))
+            _register(self, f"{p}.attn.attn.linear.weight", w_((c.n_head + 2 * c.n_query_groups) * c.head_size, E))
             _register(self, f"{p}.attn.proj.linear.weight", w_(E, c.n_head * c.head_size))
             _register(self, f"{p}.norm_2.weight", ones(E))
             _register(self, f"{p}.mlp.fc_1.linear.weight", w_(I, E))
@@ -174,6 +229,8 @@ class GPT(nn.Module):
         self.codecformer = _DepthScope(self)
         self._state: Optional["_LMState"] = None
         self._packed = None
+        self._local_states: Dict[int, "_LMState"] = {}
+        self._ns_state: Optional["_LMState"] = None      # scratch scope of the non-streaming forward_global
         self.use_cuda_graphs = True
 
     # ---- state_dict keys identical to the reference (`codecformer.` / `codecformer_text_emb.` subtrees are
@@ -191,7 +248,7 @@ class GPT(nn.Module):
         return out
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
-        sd = {}
+        sd, lora = {}, {}
         old = {"lm_head.weight": "lm_head.linear.weight"}  # llama_streaming.py:762-766 compatibility mapping
         for k, v in state_dict.items():
             k = old.get(k, k)
@@ -202,12 +259,40 @@ class GPT(nn.Module):
                          (".fc_1.weight", ".fc_1.linear.weight"), (".fc_2.weight", ".fc_2.linear.weight")):
                 if k.endswith(a) and k.startswith("transformer.h."):
                     k = k[: -len(a)] + b  # base-checkpoint names (llama_streaming.py:1000-1009, 1034-1043)
-            sd[k] = v
+            if k.endswith(".lora_A") or k.endswith(".lora_B"):
+                lora[k] = v
+            else:
+                sd[k] = v
+        self._merge_lora(sd, lora)
         self._packed = None
+        self._local_states, self._ns_state = {}, None
         return super().load_state_dict(sd, strict=strict, **kw)
+
+    def _merge_lora(self, sd, lora):
+        """W += (B @ A) * (lora_alpha / r) for every wrapped linear that carries LoRA factors: LoRALinear.merge /
+        LoRAQKVLinear.merge (llama_streaming.py:113-133, 382-385), i.e. what merge_lora_weights (:1120-1124) leaves behind."""
+        c = self.config
+        for ka in [k for k in lora if k.endswith(".lora_A")]:
+            base = ka[: -len(".lora_A")]
+            kb, kw_ = base + ".lora_B", base + ".linear.weight"
+            if kb not in lora or kw_ not in sd:
+                raise RuntimeError(f"LoRA factors for {base} without a matching lora_B / base weight")
+            A, B = lora[ka].float(), lora[kb].float()
+            W = sd[kw_]
+            if base.endswith(".attn.attn"):
+                n_en = sum((c.lora_query, c.lora_key, c.lora_value))
+                if n_en == 0:
+                    raise RuntimeError("the checkpoint holds QKV LoRA factors but Config.lora_query/key/value are all False")
+                r = A.shape[0] // n_en
+                delta = _lora_delta_qkv(A, B, c, c.lora_alpha / r, W.shape[0])
+            else:
+                r = A.shape[0]
+                delta = (B @ A) * (c.lora_alpha / r)
+            sd[kw_] = (W.float() + delta.to(W.device)).to(W.dtype)   # in-place add into the weight's dtype upstream (:133)
 
     def _apply(self, fn, *a, **kw):
         self._packed = None
+        self._local_states, self._ns_state = {}, None
         return super()._apply(fn, *a, **kw)
 
     # ---- token-id conventions (llama_streaming.py:590-634)
@@ -253,13 +338,21 @@ class GPT(nn.Module):
         y = torch.nn.functional.embedding(ids.clamp(min=0), w)
         return torch.where((ids == self.zero_token_id)[..., None], torch.zeros(1, dtype=y.dtype, device=y.device), y)
 
-    # ---- StreamingModule protocol
-    def streaming_forever(self, batch_size: int):
+    # ---- StreamingModule protocol (modules/streaming.py:33-151)
+    def _check_runnable(self):
         dev = self.device
         if dev.type != "cuda":
             raise RstnetError("GPT decode runs on CUDA only (sm_100a kernels; the CPU path is the reference itself)")
         if next(self.parameters()).dtype != torch.bfloat16:
             raise RstnetError("GPT decode runs in bfloat16: call .to(device, torch.bfloat16) as infer_no_streaming.py:104-105 does")
+
+    @property
+    def is_streaming(self) -> bool:
+        return self._state is not None
+
+    @on_own_device
+    def streaming_forever(self, batch_size: int):
+        self._check_runnable()
         self._state = _LMState(self, batch_size)
 
     @contextmanager
@@ -270,187 +363,327 @@ class GPT(nn.Module):
         finally:
             self._state = None
 
-    def reset_streaming(self):
+    @on_own_device
+    def reset_streaming(self, streams=None):
+        """reset_streaming (modules/streaming.py:115-126); `streams` (extension) restarts only those batch rows: their
+        position counters go back to 0 (the ring contents need no clearing: the position mask hides them)."""
         if self._state is None:
             raise ValueError("Trying to reset streaming, but the model wasn't streaming.")
-        self._state.reset()
+        self._state.reset(streams)
 
-    def _st(self) -> "_LMState":
+    def set_active_streams(self, mask) -> None:
+        """Extension for batched serving: hold the rows whose flag is 0 during the following steps (see codec.py)."""
         if self._state is None:
-            raise RstnetError("only the streaming decode path is implemented: call inside `with gpt.streaming(B):` "
-                              "(the full-sequence forward is the reference's own training/teacher-forcing path)")
-        return self._state
+            raise ValueError("the model is not streaming")
+        self._state.set_active(mask)
+
+    def get_streaming_state(self):
+        """modules/streaming.py:128-136: name -> state object; the whole LM is one streaming module here."""
+        return {"": self._state}
+
+    def set_streaming_state(self, state):
+        """modules/streaming.py:138-151."""
+        state = dict(state)
+        if "" not in state:
+            raise RuntimeError("Expected to find a streaming state for .")
+        st = state.pop("")
+        if state:
+            raise RuntimeError(f"Some states were not consumed: {list(state.keys())}")
+        if st is not None and (not isinstance(st, _LMState) or st.m is not self):
+            raise RuntimeError("the streaming state belongs to another model")
+        self._state = st
+
+    def check_device_errors(self, clear: bool = True) -> None:
+        """Raise if a kernel met an input the reference would have raised on (out-of-range token id, position beyond
+        block_size): device code cannot raise, it poisons its output and sets a sticky flag (synchronises)."""
+        with torch.cuda.device(self.device):
+            flags = int(_lib.lib().rstnet_device_error_flags(int(clear)))
+        if flags & 1:
+            raise IndexError("a token id was outside its embedding table (index out of range in self)")
+        if flags & 2:
+            raise IndexError(f"a position reached block_size = {self.config.block_size} (RoPE table exhausted)")
 
     # ---- reference API
     @torch.no_grad()
+    @on_own_device
     def forward_global(self, sequence: torch.Tensor):
         B, K, T = sequence.shape
         assert K == self.num_codebooks, f"Sequence shape {sequence.shape} must match the number of codebooks."
-        if T != 1:
-            raise RstnetError("streaming forward_global takes one frame per call (the reference's RoPE row select is only "
-                              "correct for T == 1 too, llama_streaming.py:972-975)")
-        return self._st().forward_global(sequence)
+        if self.max_seq_length < T:
+            raise ValueError(f"Cannot forward sequence of length {T}, max seq length is only {self.max_seq_length}.")
+        if self._state is None:
+            # non-streaming form (CausalSelfAttention.forward with state None, llama_streaming.py:946-998): positions
+            # 0..T-1 from scratch, nothing is kept afterwards
+            self._check_runnable()
+            if T > self.config.context:
+                raise RstnetError(f"non-streaming forward_global over {T} > context = {self.config.context} positions is not "
+                                  "implemented (the decode ring holds `context` keys); stream it instead")
+            st = self._ns_state
+            if st is None or st.B != B:
+                st = self._ns_state = _LMState(self, B, parts=("temporal",))
+            st.reset()
+            return st.forward_global(sequence)
+        return self._state.forward_global(sequence)
 
     @torch.no_grad()
+    @on_own_device
     def forward_codecformer(self, codecformer_cb_index: int, sequence: torch.Tensor, transformer_out: torch.Tensor):
         B, K, S = sequence.shape
         assert K == 1, f"Codebooks for Depformer streaming should be passed 1 by 1, got {K}."
         assert S == 1, f"Steps for Depformer streaming should be passed 1 by 1, got {S}."
         assert transformer_out.shape[1] == 1, "Transformer out should be a for a single step."
-        return self._st().forward_codecformer(codecformer_cb_index, sequence, transformer_out)
+        if self._state is None:
+            raise RstnetError("forward_codecformer is the streaming form: call it inside `with gpt.streaming(B):` and "
+                              "`with gpt.codecformer.streaming(B):` (forward_local is the non-streaming one)")
+        return self._state.forward_codecformer(codecformer_cb_index, sequence, transformer_out)
 
     @torch.no_grad()
+    @on_own_device
+    def forward_local(self, local_start_token: torch.Tensor, sequence: torch.Tensor, transformer_out: torch.Tensor) -> torch.Tensor:
+        """llama_streaming.py:694-725: the depth transformer over every (stream, frame) row, teacher-forced with
+        `sequence[B, dep_q, T]`, non-streaming (every step sees all earlier keys).  -> logits [B, T, dep_q, card]."""
+        self._check_runnable()
+        c = self.config
+        B, K, S = sequence.shape
+        assert K == c.dep_q, f"Sequence shape {sequence.shape} must match the moshi stream output."
+        rows = B * S
+        start = local_start_token.reshape(rows, -1).to(torch.bfloat16)
+        tout = transformer_out.reshape(rows, -1).to(torch.bfloat16)
+        ids = sequence.permute(0, 2, 1).reshape(rows, K).to(torch.int64)
+        out = torch.empty(rows, c.dep_q, c.audio_card, dtype=torch.bfloat16, device=self.device)
+        for r0 in range(0, rows, MAX_ROWS):
+            n = min(MAX_ROWS, rows - r0)
+            st = self._local_states.get(n)
+            if st is None:
+                if len(self._local_states) >= 4:
+                    self._local_states.clear()
+                st = self._local_states[n] = _LMState(self, n, parts=("depth",))
+            st.depth_local(start[r0:r0 + n], ids[r0:r0 + n], tout[r0:r0 + n], out[r0:r0 + n])
+        return out.view(B, S, c.dep_q, c.audio_card)
+
+    @torch.no_grad()
+    @on_own_device
     def forward_step(self, sequence: torch.Tensor, *, use_sampling: bool = True, temp_text: float = 0.7, top_k_text: int = 25,
-                     temp: float = 0.8, top_k: int = 30, audio_valid=2049) -> torch.Tensor:
+                     temp: float = 0.8, top_k: int = 30, audio_valid=2049, depth_ring_quirk: bool = True) -> torch.Tensor:
         """One generated frame: temporal step on sequence[B,9,1], text token, then the 8 depth steps, each sampled
-        on the device (sample_token / sample_token_audio, utils/sampling.py:85-154).  Returns tokens [B, 9]
-        (text, audio_0..7).  With use_cuda_graphs the whole frame is a single graph replay."""
-        return self._st().forward_step(sequence, use_sampling, temp_text, top_k_text, temp, top_k, audio_valid)
+        on the device (sample_token / sample_token_audio[_2048], utils/sampling.py:85-154: use_sampling False ->
+        argmax over the whole card; True -> temperature + top-k (top_k == 0: plain multinomial) over ids <
+        audio_valid).  Returns tokens [B, 9] (text, audio_0..7).  With use_cuda_graphs the whole frame is a single
+        graph replay.  depth_ring_quirk False evaluates the depth steps as forward_local does (see there)."""
+        if self._state is None:
+            raise RstnetError("forward_step is a streaming call: use it inside `with gpt.streaming(B):`")
+        return self._state.forward_step(sequence, use_sampling, temp_text, top_k_text, temp, top_k, audio_valid, depth_ring_quirk)
+
+    @torch.no_grad()
+    @on_own_device
+    def prefill(self, sequence: torch.Tensor) -> None:
+        """Feed sequence[B,9,T] through the temporal transformer (KV rings + positions advance by T) without producing
+        outputs: what a prompt needs before generation starts (no lm_head, no depth steps)."""
+        if self._state is None:
+            raise RstnetError("prefill is a streaming call: use it inside `with gpt.streaming(B):`")
+        self._state.forward_global(sequence, want_outputs=False)
 
     def forward(self, *a, **kw):
-        raise NotImplementedError("training / teacher-forcing forward is out of scope; use the streaming decode API")
+        raise NotImplementedError("training / teacher-forcing forward is out of scope; use forward_global / forward_local")
 
 
 class _LMState:
-    """Buffers, KV rings, GEMM plans of one `streaming(B)` scope."""
+    """Buffers, KV rings, GEMM plans of one `streaming(B)` scope.  Rows of every activation buffer are (position,
+    stream) pairs, position-major: row = tl * B + b.  The decode state has tn == 1; a prefill chunk state (`parent` set)
+    has tn > 1 rows per stream and shares the parent's KV rings and position counters; a `parts == ("depth",)` state
+    only holds the depth transformer (forward_local)."""
 
-    def __init__(self, m: GPT, B: int):
+    def __init__(self, m: GPT, B: int, tn: int = 1, parent: Optional["_LMState"] = None, parts=("temporal", "depth")):
         c, dev = m.config, m.device
-        self.m, self.B, self.c = m, B, c
+        self.m, self.B, self.c, self.tn = m, B, c, tn
+        M = self.M = B * tn
+        if M > MAX_ROWS:
+            raise RstnetError(f"at most {MAX_ROWS} rows per launch sequence (got {B} streams x {tn} positions)")
         bf = torch.bfloat16
         P = {k: v for k, v in m.named_parameters()}
         E, V, I, D, H = c.n_embd, c.padded_vocab_size, c.intermediate_size, c.codecformer_dim, c.ff_hidden
-        nh, hs = c.n_head, c.head_size
+        nh, nkv, hs = c.n_head, c.n_query_groups, c.head_size
         self.cap = c.context
+        Hp = -(-H // 64) * 64      # the GEMM's K granularity: pad the gating hidden size with zero weights
+        self.Hp = Hp
 
         def z(*shape, dtype=bf):
             return torch.zeros(*shape, dtype=dtype, device=dev)
 
-        # activations
-        self.seq = z(B, c.n_q + 1, dtype=torch.int64)
-        self.x, self.xn, self.q, self.att = z(B, E), z(B, E), z(B, nh * hs), z(B, nh * hs)
-        self.qkv, self.ab, self.hmid = z(B, 3 * nh * hs), z(B, 2 * I), z(B, I)
-        self.out, self.logits = z(B, E), z(B, V)
-        self.tout = z(B, E)
-        self.demb, self.dx, self.dn, self.datt = z(B, D), z(B, D), z(B, D), z(B, D)
-        self.dqkv, self.dab, self.dh, self.dlogits = z(B, 3 * D), z(B, 2 * H), z(B, H), z(B, c.audio_card)
-        self.tokens = z(B, c.dep_q + 1, dtype=torch.int64)
-        self._idbuf = z(B, dtype=torch.int64)
-        self.offset = z(1, dtype=torch.int64)
-        self.frame_counter = z(1, dtype=torch.int64)
-        # KV rings (k/v stored per head like the reference: [2,B,nh,cap,hs], lit_model.py:607-615)
-        self.kv = [z(2, B, nh, self.cap, hs) for _ in range(c.n_layer)]
-        hd = D // c.codecformer_heads
-        self.dkv = [z(2, B, c.codecformer_heads, c.dep_q, hd) for _ in range(c.codecformer_layers)]
-        # RoPE tables in the model dtype (the reference's buffers are cast by .to(bfloat16))
-        theta = 1.0 / (c.rope_base ** (torch.arange(0, hs, 2).float() / hs))
-        idx_theta = torch.outer(torch.arange(c.block_size) / 1, theta).repeat(1, 2)
-        self.cos, self.sin = torch.cos(idx_theta).to(bf).to(dev).contiguous(), torch.sin(idx_theta).to(bf).to(dev).contiguous()
-        # embedding table pointer array
-        self.tables = [P[f"input_emb.{i}.weight"] for i in range(c.n_q)]
-        self.table_ptrs = torch.tensor([t.data_ptr() for t in self.tables], dtype=torch.int64, device=dev)
-        self.wte = P["transformer.wte.weight"]
-        # split-K workspace shared by all GEMM plans (launches are stream-ordered)
-        self.ws = torch.empty(8 * B * max(3 * E, 2 * I, 4096), dtype=torch.float32, device=dev)
         if m._packed is None:
-            m._packed = {f"fc12.{l}": torch.cat([P[f"transformer.h.{l}.mlp.fc_1.linear.weight"],
-                                                 P[f"transformer.h.{l}.mlp.fc_2.linear.weight"]], 0).contiguous()
-                         for l in range(c.n_layer)}
-        wsmax = max(3 * E, 2 * I, 4096)
+            pk = {f"fc12.{l}": torch.cat([P[f"transformer.h.{l}.mlp.fc_1.linear.weight"],
+                                          P[f"transformer.h.{l}.mlp.fc_2.linear.weight"]], 0).contiguous()
+                  for l in range(c.n_layer)}
+            if Hp != H:
+                for l in range(c.codecformer_layers):
+                    for k in range(c.dep_q):
+                        w_in = P[f"codecformer_.layers.{l}.gating.{k}.linear_in.weight"]
+                        w_out = P[f"codecformer_.layers.{l}.gating.{k}.linear_out.weight"]
+                        gi = z(2 * Hp, D)
+                        gi[:H], gi[Hp:Hp + H] = w_in[:H], w_in[H:]
+                        go = z(D, Hp)
+                        go[:, :H] = w_out
+                        pk[f"gin.{l}.{k}"], pk[f"gout.{l}.{k}"] = gi, go
+            m._packed = pk
+        wsmax = max((nh + 2 * nkv) * hs, 2 * I, 4096, 3 * D, 2 * Hp)
+        self.ws = parent.ws if parent is not None and parent.M >= M else torch.empty(8 * M * wsmax, dtype=torch.float32, device=dev)
         G = lambda X, W, out, R=None, **kw: SkinnyGemm(X, W, out, R, self.ws if W.shape[0] <= wsmax else None, **kw)
-        L_ = c.n_layer
-        n1 = [P[f"transformer.h.{l}.norm_1.weight"] for l in range(L_)]
-        n2 = [P[f"transformer.h.{l}.norm_2.weight"] for l in range(L_)]
-        self.ln_f = P["transformer.ln_f.weight"]
-        self.n1_first = n1[0]
-        self.layers = []
-        for l in range(L_):
-            p = f"transformer.h.{l}"
-            last = l == L_ - 1
-            self.layers.append(dict(
-                qkv=G(self.xn, P[f"{p}.attn.attn.linear.weight"], self.qkv),
-                # x = attn + x ; xn = norm_2(x)   (Block.forward, llama_streaming.py:846-849) in the GEMM's finalize
-                proj=G(self.att, P[f"{p}.attn.proj.linear.weight"], self.x, self.x, norm_w=n2[l], aux=self.xn, eps=c.norm_eps),
-                # hmid = silu(fc_1 x) * fc_2 x   (LLaMAMLP, lit_model.py:399-403)
-                fc=G(self.xn, m._packed[f"fc12.{l}"], None, silu_out=self.hmid),
-                # x = mlp + x ; xn = norm_1 of the next block (or ln_f -> transformer_out)
-                down=G(self.hmid, P[f"{p}.mlp.proj.linear.weight"], self.x, self.x, norm_w=self.ln_f if last else n1[l + 1],
-                       aux=self.out if last else self.xn, eps=c.norm_eps)))
-        self.head = G(self.out, P["lm_head.linear.weight"], self.logits)
-        # depth transformer: per-codebook-step weight slabs
-        self.text_emb = P["codecformer_text_emb_.weight"]
-        self.dep_emb = [P[f"codecformer_emb.{i}.weight"] for i in range(c.dep_q - 1)]
-        Ld = c.codecformer_layers
-        a1 = [P[f"codecformer_.layers.{l}.norm1.alpha"].view(-1) for l in range(Ld)]
-        a2 = [P[f"codecformer_.layers.{l}.norm2.alpha"].view(-1) for l in range(Ld)]
-        self.dsteps = []
-        for k in range(c.dep_q):
-            layers = []
-            for l in range(Ld):
-                p = f"codecformer_.layers.{l}"
-                w_in = P[f"{p}.self_attn.in_proj_weight"].view(c.dep_q, 3 * D, D)[k]
-                w_out = P[f"{p}.self_attn.out_proj.weight"].view(c.dep_q, D, D)[k]
-                nxt = dict(norm_w=a1[l + 1], aux=self.dn, eps=1e-8, kyutai=True) if l + 1 < Ld else {}
-                layers.append(dict(
-                    qkv=G(self.dn, w_in, self.dqkv),
-                    out=G(self.datt, w_out, self.dx, self.dx, norm_w=a2[l], aux=self.dn, eps=1e-8, kyutai=True),
-                    gin=G(self.dn, P[f"{p}.gating.{k}.linear_in.weight"], None, silu_out=self.dh),
-                    gout=G(self.dh, P[f"{p}.gating.{k}.linear_out.weight"], self.dx, self.dx, **nxt)))
-            self.dsteps.append(dict(
-                inp=G(self.tout, P[f"codecformer_in.{k}.weight"], self.dx, self.demb, norm_w=a1[0], aux=self.dn, eps=1e-8, kyutai=True),
-                layers=layers, head=G(self.dx, P[f"audio_linears.{k}.weight"], self.dlogits)))
-        self.depth_step: Optional[int] = None
         self.graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self.warm: Dict[tuple, int] = {}
         self.seed = 1234
+        self.depth_step: Optional[int] = None
+        self.children: Dict[int, "_LMState"] = {}
+        self.has_temporal = "temporal" in parts
 
-    def reset(self):
-        self.offset.zero_()
-        self.frame_counter.zero_()
+        if self.has_temporal:
+            self.seq = z(M, c.n_q + 1, dtype=torch.int64)
+            self.x, self.xn, self.q, self.att = z(M, E), z(M, E), z(M, nh * hs), z(M, nh * hs)
+            self.qkv, self.hmid = z(M, (nh + 2 * nkv) * hs), z(M, I)
+            self.out, self.logits = z(M, E), z(M, V)
+            if parent is None:
+                # one position counter per stream (per-stream reset / admission), mirrored on the host for the
+                # block_size check (under graph replay the device cannot raise)
+                self.offset = z(B, dtype=torch.int64)
+                self.pos_host = np.zeros(B, dtype=np.int64)
+                # advance flags: a stream with 0 is HELD by the next steps (frame scheduler rows without input)
+                self.active = torch.ones(B, dtype=torch.int64, device=dev)
+                self.active_host = np.ones(B, dtype=np.int64)
+                # KV rings, one K/V row per KV GROUP: [2, B, n_kv, cap, hs] (lit_model.py:607-615 stores n_head copies)
+                self.kv = [z(2, B, nkv, self.cap, hs) for _ in range(c.n_layer)]
+                # RoPE tables in the model dtype (the reference's buffers are cast by .to(bfloat16)); lit_model.py:441-488
+                n = c.rope_n_elem
+                theta = 1.0 / (c.rope_base ** (torch.arange(0, n, 2).float() / n))
+                if c.rope_adjustments is not None:
+                    ec = c.rope_adjustments
+                    wavelen = 2 * torch.pi / theta
+                    ratio = ec["original_max_seq_len"] / wavelen
+                    smooth = torch.clamp((ratio - ec["low_freq_factor"]) / (ec["high_freq_factor"] - ec["low_freq_factor"]), min=0.0, max=1.0)
+                    theta = (1 - smooth) * (theta / ec["factor"]) + smooth * theta
+                idx_theta = torch.outer(torch.arange(c.block_size) / c.rope_condense_ratio, theta).repeat(1, 2)
+                self.cos, self.sin = torch.cos(idx_theta).to(bf).to(dev).contiguous(), torch.sin(idx_theta).to(bf).to(dev).contiguous()
+            else:
+                self.offset, self.pos_host, self.kv, self.cos, self.sin = parent.offset, parent.pos_host, parent.kv, parent.cos, parent.sin
+                self.active, self.active_host = parent.active, parent.active_host
+            self.tables = [P[f"input_emb.{i}.weight"] for i in range(c.n_q)]
+            self.table_ptrs = torch.tensor([t.data_ptr() for t in self.tables], dtype=torch.int64, device=dev)
+            self.wte = P["transformer.wte.weight"]
+            L_ = c.n_layer
+            n1 = [P[f"transformer.h.{l}.norm_1.weight"] for l in range(L_)]
+            n2 = [P[f"transformer.h.{l}.norm_2.weight"] for l in range(L_)]
+            self.ln_f = P["transformer.ln_f.weight"]
+            self.n1_first = n1[0]
+            self.layers = []
+            for l in range(L_):
+                p = f"transformer.h.{l}"
+                last = l == L_ - 1
+                self.layers.append(dict(
+                    qkv=G(self.xn, P[f"{p}.attn.attn.linear.weight"], self.qkv),
+                    # x = attn + x ; xn = norm_2(x)   (Block.forward, llama_streaming.py:846-849) in the GEMM's finalize
+                    proj=G(self.att, P[f"{p}.attn.proj.linear.weight"], self.x, self.x, norm_w=n2[l], aux=self.xn, eps=c.norm_eps),
+                    # hmid = silu(fc_1 x) * fc_2 x   (LLaMAMLP, lit_model.py:399-403)
+                    fc=G(self.xn, m._packed[f"fc12.{l}"], None, silu_out=self.hmid),
+                    # x = mlp + x ; xn = norm_1 of the next block (or ln_f -> transformer_out)
+                    down=G(self.hmid, P[f"{p}.mlp.proj.linear.weight"], self.x, self.x, norm_w=self.ln_f if last else n1[l + 1],
+                           aux=self.out if last else self.xn, eps=c.norm_eps)))
+            self.head = G(self.out, P["lm_head.linear.weight"], self.logits)
+
+        if "depth" in parts:
+            self.tout = z(M, E)
+            self.demb, self.dx, self.dn, self.datt = z(M, D), z(M, D), z(M, D), z(M, D)
+            self.dqkv, self.dh, self.dlogits = z(M, 3 * D), z(M, Hp), z(M, c.audio_card)
+            self.tokens = z(M, c.dep_q + 1, dtype=torch.int64)
+            self._idbuf = z(M, dtype=torch.int64)
+            self.frame_counter = z(1, dtype=torch.int64)
+            hd = D // c.codecformer_heads
+            self.dkv = [z(2, M, c.codecformer_heads, c.dep_q, hd) for _ in range(c.codecformer_layers)]
+            # depth transformer: per-codebook-step weight slabs
+            self.text_emb = P["codecformer_text_emb_.weight"]
+            self.dep_emb = [P[f"codecformer_emb.{i}.weight"] for i in range(c.dep_q - 1)]
+            Ld = c.codecformer_layers
+            a1 = [P[f"codecformer_.layers.{l}.norm1.alpha"].view(-1) for l in range(Ld)]
+            a2 = [P[f"codecformer_.layers.{l}.norm2.alpha"].view(-1) for l in range(Ld)]
+            self.dsteps = []
+            for k in range(c.dep_q):
+                layers = []
+                for l in range(Ld):
+                    p = f"codecformer_.layers.{l}"
+                    w_in = P[f"{p}.self_attn.in_proj_weight"].view(c.dep_q, 3 * D, D)[k]
+                    w_out = P[f"{p}.self_attn.out_proj.weight"].view(c.dep_q, D, D)[k]
+                    g_in = m._packed.get(f"gin.{l}.{k}", P[f"{p}.gating.{k}.linear_in.weight"])
+                    g_out = m._packed.get(f"gout.{l}.{k}", P[f"{p}.gating.{k}.linear_out.weight"])
+                    nxt = dict(norm_w=a1[l + 1], aux=self.dn, eps=1e-8, kyutai=True) if l + 1 < Ld else {}
+                    layers.append(dict(
+                        qkv=G(self.dn, w_in, self.dqkv),
+                        out=G(self.datt, w_out, self.dx, self.dx, norm_w=a2[l], aux=self.dn, eps=1e-8, kyutai=True),
+                        gin=G(self.dn, g_in, None, silu_out=self.dh),
+                        gout=G(self.dh, g_out, self.dx, self.dx, **nxt)))
+                self.dsteps.append(dict(
+                    inp=G(self.tout, P[f"codecformer_in.{k}.weight"], self.dx, self.demb, norm_w=a1[0], aux=self.dn, eps=1e-8, kyutai=True),
+                    layers=layers, head=G(self.dx, P[f"audio_linears.{k}.weight"], self.dlogits)))
+
+    def reset(self, streams=None):
+        if streams is None:
+            self.offset.zero_()
+            self.pos_host[:] = 0
+        else:
+            idx = torch.as_tensor(streams, dtype=torch.int64).reshape(-1)
+            if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= self.B):
+                raise RstnetError(f"stream index outside [0, {self.B})")
+            self.offset[idx.to(self.offset.device)] = 0
+            self.pos_host[idx.numpy()] = 0
+        if hasattr(self, "frame_counter"):
+            self.frame_counter.zero_()
         self.depth_step = None
 
     # ---- launch sequences -------------------------------------------------------------------
-    def _temporal(self):
-        c, B, L = self.c, self.B, _lib.lib()
+    def _temporal(self, head: bool = True):
+        c, B, M, L = self.c, self.B, self.M, _lib.lib()
         st = ops._stream()
         E = c.n_embd
-        _lib.check(L.rstnet_lm_embed_sum_bf16(self.seq.data_ptr(), c.n_q + 1, self.wte.data_ptr(), self.table_ptrs.data_ptr(),
-                                              c.n_q, E, self.x.data_ptr(), B, st), "lm_embed_sum")
-        _lib.check(L.rstnet_lm_rms_norm_bf16(self.x.data_ptr(), self.n1_first.data_ptr(), self.xn.data_ptr(), B, E, c.norm_eps, 0, st), "rms")
+        ost = 1 if self.offset.numel() > 1 else 0
+        _lib.check(L.rstnet_lm_embed_sum_bf16(self.seq.data_ptr(), c.n_q + 1, self.wte.data_ptr(), self.wte.shape[0],
+                                              self.table_ptrs.data_ptr(), self.tables[0].shape[0], c.n_q, E, self.x.data_ptr(), M, st),
+                   "lm_embed_sum")
+        _lib.check(L.rstnet_lm_rms_norm_bf16(self.x.data_ptr(), self.n1_first.data_ptr(), self.xn.data_ptr(), M, E, c.norm_eps, 0, st), "rms")
         for l, ly in enumerate(self.layers):
             ly["qkv"].run()
-            _lib.check(L.rstnet_lm_rope_kv_append_bf16(self.qkv.data_ptr(), self.cos.data_ptr(), self.sin.data_ptr(),
-                                                       self.offset.data_ptr(), self.q.data_ptr(), self.kv[l].data_ptr(), B,
-                                                       c.n_head, c.head_size, self.cap, st), "rope_kv")
-            _lib.check(L.rstnet_lm_ring_decode_attention_bf16(self.q.data_ptr(), self.kv[l].data_ptr(), self.offset.data_ptr(),
-                                                              self.att.data_ptr(), B, c.n_head, c.head_size, self.cap, c.context, st),
-                       "attention")
+            _lib.check(L.rstnet_lm_rope_kv_append_bf16(self.qkv.data_ptr(), self.cos.data_ptr(), self.sin.data_ptr(), self.cos.shape[0],
+                                                       c.rope_n_elem, self.offset.data_ptr(), ost, self.q.data_ptr(),
+                                                       self.kv[l].data_ptr(), M, B, c.n_head, c.n_query_groups, c.head_size, self.cap, st),
+                       "rope_kv")
+            _lib.check(L.rstnet_lm_ring_decode_attention_bf16(self.q.data_ptr(), self.kv[l].data_ptr(), self.offset.data_ptr(), ost,
+                                                              self.att.data_ptr(), M, B, c.n_head, c.n_query_groups, c.head_size,
+                                                              self.cap, c.context, st), "attention")
             ly["proj"].run()   # + residual + norm_2 -> xn
             ly["fc"].run()     # + SiLU gating -> hmid
             ly["down"].run()   # + residual + next pre-norm -> xn (last layer: ln_f -> transformer_out)
-        self.head.run()
-        ops.counter_add(self.offset, 1)
+        if head:
+            self.head.run()
+        ops.counter_add(self.offset, self.tn, self.active)
 
-    def _depth(self, k: int, ids: torch.Tensor, id_stride: int):
-        c, B, L = self.c, self.B, _lib.lib()
+    def _depth(self, k: int, ids: Optional[torch.Tensor], id_stride: int, quirk: bool = True):
+        """ids None: the step's input embedding is already in self.demb (forward_local passes features for step 0)."""
+        c, M, L = self.c, self.M, _lib.lib()
         st = ops._stream()
         D = c.codecformer_dim
-        table = self.text_emb if k == 0 else self.dep_emb[k - 1]
-        _lib.check(L.rstnet_lm_embed_rows_bf16(ids.data_ptr(), id_stride, table.data_ptr(), D, self.demb.data_ptr(), B, st), "embed_rows")
+        if ids is not None:
+            table = self.text_emb if k == 0 else self.dep_emb[k - 1]
+            _lib.check(L.rstnet_lm_embed_rows_bf16(ids.data_ptr(), id_stride, table.data_ptr(), table.shape[0], D, self.demb.data_ptr(), M, st),
+                       "embed_rows")
         ds = self.dsteps[k]
         ds["inp"].run()        # dx = in_k(transformer_out) + emb ; dn = norm1_0(dx)
         hd = D // c.codecformer_heads
         for l, ly in enumerate(ds["layers"]):
             ly["qkv"].run()
-            _lib.check(L.rstnet_lm_depth_attention_bf16(self.dqkv.data_ptr(), self.dkv[l].data_ptr(), self.datt.data_ptr(), B,
-                                                        c.codecformer_heads, hd, c.dep_q, k, st), "depth_attention")
+            _lib.check(L.rstnet_lm_depth_attention_bf16(self.dqkv.data_ptr(), self.dkv[l].data_ptr(), self.datt.data_ptr(), M,
+                                                        c.codecformer_heads, hd, c.dep_q, k, int(quirk), st), "depth_attention")
             ly["out"].run()    # dx += out_k(att) ; dn = norm2(dx)
             ly["gin"].run()    # dh = silu(a) * b
             ly["gout"].run()   # dx += out(dh) ; dn = norm1 of the next layer
         ds["head"].run()
 
     def _sample(self, logits: torch.Tensor, V: int, n_valid: int, top_k: int, temp: float, col: int, salt: int):
-        _lib.check(_lib.lib().rstnet_lm_sample_bf16(logits.data_ptr(), self.B, V, n_valid, top_k, float(temp), self.seed + salt,
+        _lib.check(_lib.lib().rstnet_lm_sample_bf16(logits.data_ptr(), self.M, V, n_valid, top_k, float(temp), self.seed + salt,
                                                     self.frame_counter.data_ptr(), self.tokens.data_ptr() + 8 * col,
                                                     self.c.dep_q + 1, ops._stream()), "sample")
 
@@ -471,12 +704,69 @@ class _LMState:
             self.graphs[key] = g
         g.replay()
 
+    def _advance_host(self, n: int):
+        """Host mirror of the position counters: the reference's cos.index_select raises past block_size
+        (llama_streaming.py:972-975); a graph replay cannot, so the check happens here, before the launch."""
+        if int(self.pos_host.max()) + n > self.cos.shape[0]:
+            raise IndexError(f"position {int(self.pos_host.max()) + n - 1} is beyond block_size = {self.cos.shape[0]} "
+                             "(RoPE table exhausted; reset the stream or raise Config.block_size)")
+        self.pos_host += n * self.active_host
+
+    def set_active(self, mask):
+        """mask [B]: streams with 0 are held by the next steps (they run through the kernels, but their position does not
+        advance; the K/V row written at the held position is overwritten by the stream's next real step)."""
+        if mask is None:
+            self.active.fill_(1)
+            self.active_host[:] = 1
+        else:
+            mk = torch.as_tensor(mask).to(dtype=torch.int64).reshape(self.B).cpu()
+            self.active_host[:] = mk.numpy()
+            self.active.copy_(mk.to(self.active.device))
+
     # ---- API ----------------------------------------------------------------------------------
-    def forward_global(self, sequence: torch.Tensor):
-        self.seq.copy_(sequence[:, :, 0])
-        self._replay(("temporal",), self._temporal)
+    def forward_global(self, sequence: torch.Tensor, want_outputs: bool = True):
         c = self.c
-        return self.out.view(self.B, 1, c.n_embd).clone(), self.logits.view(self.B, 1, c.padded_vocab_size).clone()
+        B, K, T = sequence.shape
+        if B != self.B:
+            raise RstnetError(f"streaming batch size is {self.B}, got {B}")
+        if T == 1:
+            self._advance_host(1)
+            self.seq.copy_(sequence[:, :, 0])
+            if want_outputs:
+                self._replay(("temporal",), self._temporal)
+                return self.out.view(B, 1, c.n_embd).clone(), self.logits.view(B, 1, c.padded_vocab_size).clone()
+            self._replay(("temporal_nohead",), lambda: self._temporal(head=False))
+            return None
+        # prefill: chunks of tn consecutive positions for all streams (tn * B <= MAX_ROWS rows per launch sequence).
+        # A multi-position chunk appends all its keys before any of its queries run, so it must not overwrite a ring slot
+        # one of those queries still needs: tn > 1 only while the ring does not wrap inside the chunk.
+        outs, logits = [], []
+        per = max(1, MAX_ROWS // B)
+        t = 0
+        while t < T:
+            tn = min(per, T - t)
+            if tn > 1 and int(self.pos_host.max()) + tn > self.cap:
+                tn = 1
+            if tn == 1:
+                r = self.forward_global(sequence[:, :, t:t + 1], want_outputs)
+                if want_outputs:
+                    outs.append(r[0]); logits.append(r[1])
+            else:
+                ch = self.children.get(tn)
+                if ch is None:
+                    if len(self.children) >= 2:      # keep at most two chunk shapes alive (full chunk + one tail)
+                        self.children.pop(next(iter(self.children)))
+                    ch = self.children[tn] = _LMState(self.m, B, tn=tn, parent=self, parts=("temporal",))
+                self._advance_host(tn)
+                ch.seq.copy_(sequence[:, :, t:t + tn].permute(2, 0, 1).reshape(tn * B, K))
+                ch._temporal(head=want_outputs)
+                if want_outputs:
+                    outs.append(ch.out.view(tn, B, c.n_embd).permute(1, 0, 2).clone())
+                    logits.append(ch.logits.view(tn, B, c.padded_vocab_size).permute(1, 0, 2).clone())
+            t += tn
+        if not want_outputs:
+            return None
+        return torch.cat(outs, 1), torch.cat(logits, 1)
 
     def forward_codecformer(self, k: int, sequence: torch.Tensor, transformer_out: torch.Tensor):
         if self.depth_step is None:
@@ -489,22 +779,43 @@ class _LMState:
         self.depth_step += 1
         return self.dlogits.view(self.B, 1, 1, self.c.audio_card).clone()
 
-    def forward_step(self, sequence, use_sampling, temp_text, top_k_text, temp, top_k, audio_valid):
+    def depth_local(self, start: torch.Tensor, ids: torch.Tensor, tout: torch.Tensor, out: torch.Tensor):
+        """forward_local on self.M rows: start [M, D] features of step 0, ids [M, dep_q] teacher-forced tokens
+        (column k-1 feeds step k), tout [M, E]; writes out [M, dep_q, card]."""
         c = self.c
+        self.tout.copy_(tout)
+        self.tokens[:, :c.dep_q].copy_(ids)
+        for k in range(c.dep_q):
+            if k == 0:
+                self.demb.copy_(start)
+                self._depth(0, None, 0, quirk=False)
+            else:
+                self._depth(k, self.tokens[:, k - 1], c.dep_q + 1, quirk=False)
+            out[:, k].copy_(self.dlogits)
+
+    def forward_step(self, sequence, use_sampling, temp_text, top_k_text, temp, top_k, audio_valid, quirk=True):
+        c = self.c
+        if sequence.shape[0] != self.B or sequence.shape[2] != 1:
+            raise RstnetError(f"forward_step takes sequence [{self.B}, {c.n_q + 1}, 1], got {tuple(sequence.shape)}")
+        self._advance_host(1)
         self.seq.copy_(sequence[:, :, 0])
-        tk_text = top_k_text if use_sampling else 0
-        tk = top_k if use_sampling else 0
+        # kernel convention: 0 = argmax, k > 0 = top-k, -1 = multinomial over the whole (valid) support
+        sampling_text = use_sampling and temp_text > 0.0
+        sampling = use_sampling and temp > 0.0
+        tk_text = (top_k_text if top_k_text > 0 else -1) if sampling_text else 0
+        tk = (top_k if top_k > 0 else -1) if sampling else 0
+        valid = tuple(audio_valid) if isinstance(audio_valid, (tuple, list)) else (audio_valid,) * c.dep_q
+        if not sampling:
+            valid = (c.audio_card,) * c.dep_q   # the 2048 / 2049 masks exist on the sampling path only (sampling.py:107-154)
 
         def frame():
             self._temporal()
-            self._sample(self.logits, c.padded_vocab_size, c.padded_vocab_size, tk_text, temp_text, 0, 0)
-            ops_t = self.out
-            self.tout.copy_(ops_t)
+            self._sample(self.logits, c.padded_vocab_size, c.padded_vocab_size, tk_text, temp_text if sampling_text else 1.0, 0, 0)
+            self.tout.copy_(self.out)
             for k in range(c.dep_q):
-                self._depth(k, self.tokens[:, k], c.dep_q + 1)
-                av = audio_valid[k] if isinstance(audio_valid, (tuple, list)) else audio_valid
-                self._sample(self.dlogits, c.audio_card, min(av, c.audio_card), tk, temp, k + 1, k + 1)
+                self._depth(k, self.tokens[:, k], c.dep_q + 1, quirk=quirk)
+                self._sample(self.dlogits, c.audio_card, min(valid[k], c.audio_card), tk, temp if sampling else 1.0, k + 1, k + 1)
             ops.counter_add(self.frame_counter, 1)
 
-        self._replay(("frame", tk_text, float(temp_text), tk, float(temp), tuple(audio_valid) if isinstance(audio_valid, (tuple, list)) else audio_valid), frame)
+        self._replay(("frame", tk_text, float(temp_text), tk, float(temp), valid, bool(quirk)), frame)
         return self.tokens.clone()

@@ -128,29 +128,40 @@ def convtr1d_depthwise(x, x_bs, x_ts, w, out, out_off, out_bs, out_ts, batch, T,
                                                         out_bs, out_ts, batch, T, Cch, stride, _stream()), "convtr1d_depthwise")
 
 
-def rows_fill(buf, bs, batch, Cch, row0, nrows, mode=0, src_row=0, only_if_zero=None):
+def rows_fill(buf, bs, batch, Cch, row0, nrows, mode=0, src_row=0, only_if_zero=None, channels_per_stream=0):
+    """only_if_zero: int64 counter(s); one element = shared, more = one per stream (see the header)."""
     _cuda(buf)
+    oz_stride = 1 if (only_if_zero is not None and only_if_zero.numel() > 1) else 0
     _lib.check(_lib.lib().rstnet_rows_fill_f32(buf.data_ptr(), bs, batch, Cch, row0, nrows, mode, src_row,
-                                               _p(only_if_zero), _stream()), "rows_fill")
+                                               _p(only_if_zero), oz_stride, channels_per_stream, _stream()), "rows_fill")
 
 
-def rows_copy_table(table_dev: torch.Tensor, n_entries: int, batch: int):
-    _lib.check(_lib.lib().rstnet_rows_copy_table_f32(table_dev.data_ptr(), n_entries, batch, _stream()), "rows_copy_table")
+def rows_copy_table(table_dev: torch.Tensor, n_entries: int, batch: int, active: Optional[torch.Tensor] = None):
+    _lib.check(_lib.lib().rstnet_rows_copy_table_f32(table_dev.data_ptr(), n_entries, batch, _p(active), _stream()), "rows_copy_table")
 
 
 def make_copy_table(entries, device) -> torch.Tensor:
-    """entries: list of (tensor, batch_stride, C, src_row, dst_row, nrows) -> device uint8 tensor."""
+    """entries: list of (tensor, batch_stride, C, src_row, dst_row, nrows, channels_per_stream) -> device uint8 tensor."""
     arr = (RowCopy * len(entries))()
-    for i, (t, bs, c, s, d, n) in enumerate(entries):
+    for i, (t, bs, c, s, d, n, cps) in enumerate(entries):
         if n > 0 and not (s >= d):
             raise _lib.RstnetError("carry copy must move rows towards the front (src_row >= dst_row)")
         arr[i].buf, arr[i].batch_stride, arr[i].C, arr[i].src_row, arr[i].dst_row, arr[i].nrows = t.data_ptr(), bs, c, s, d, n
+        arr[i].cps = cps
     raw = bytes(arr)
     return torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
 
 
-def counter_add(counter: torch.Tensor, delta: int):
-    _lib.check(_lib.lib().rstnet_counter_add(counter.data_ptr(), delta, _stream()), "counter_add")
+def counter_add(counter: torch.Tensor, delta: int, active: Optional[torch.Tensor] = None):
+    """every element of the int64 counter tensor += delta (one shared counter or one per stream; elements whose
+    `active` flag is 0 are held)"""
+    if active is not None and active.numel() != counter.numel():
+        active = None
+    _lib.check(_lib.lib().rstnet_counter_add(counter.data_ptr(), delta, counter.numel(), _p(active), _stream()), "counter_add")
+
+
+def _ostride(offset: torch.Tensor) -> int:
+    return 1 if offset.numel() > 1 else 0
 
 
 def layer_norm(x, x_off, x_bs, w, b, y, batch, rows, dim, eps):
@@ -161,13 +172,13 @@ def layer_norm(x, x_off, x_bs, w, b, y, batch, rows, dim, eps):
 
 def rope_kv_append(qkv, q_bs, q_ts, kv, offset, freqs, batch, T, H, D, cap):
     _cuda(qkv, kv, offset, freqs)
-    _lib.check(_lib.lib().rstnet_rope_kv_append_f32(qkv.data_ptr(), q_bs, q_ts, kv.data_ptr(), offset.data_ptr(),
+    _lib.check(_lib.lib().rstnet_rope_kv_append_f32(qkv.data_ptr(), q_bs, q_ts, kv.data_ptr(), offset.data_ptr(), _ostride(offset),
                                                     freqs.data_ptr(), batch, T, H, D, cap, _stream()), "rope_kv_append")
 
 
 def ring_attention(qkv, q_bs, q_ts, kv, offset, out, o_bs, o_ts, batch, T, H, D, cap, context, linear):
     _cuda(qkv, kv, offset, out)
-    _lib.check(_lib.lib().rstnet_ring_attention_f32(qkv.data_ptr(), q_bs, q_ts, kv.data_ptr(), offset.data_ptr(),
+    _lib.check(_lib.lib().rstnet_ring_attention_f32(qkv.data_ptr(), q_bs, q_ts, kv.data_ptr(), offset.data_ptr(), _ostride(offset),
                                                     out.data_ptr(), o_bs, o_ts, batch, T, H, D, cap, context, int(linear),
                                                     _stream()), "ring_attention")
 
