@@ -12,6 +12,16 @@ from pinned host memory and reads tokens + waveform back each frame.  Multi-GPU:
 across ranks with no data-path collective (weak scaling); timing = max over ranks.
 `--impl reference` times the reference's CPU implementation of the same path (the oracle port, torch
 CPU fp32 with all host threads) on a bounded sample.
+
+Next to the headline (N = 1 only, extra keys, each its own unit of work and outside the headline's timed region):
+  steady_state        the same pass with the codec transformers' rings already full (context 250), i.e. what a long-running
+                      server sees; the headline's 10 s streams start cold;
+  lm_decode           BASELINE configs[2]: one 7B decode step, B = 64, KV ring 2048 (wrapped);
+  cfg4_infer          BASELINE configs[3]: Mimi encode -> InferenceImp (prefill + 1000 generated frames) -> Mimi decode, B = 32;
+  cfg5_duplex         BASELINE configs[4] on one GPU: batched real-time loop (codec encode -> LM frame -> codec decode per 80 ms
+                      tick, rstnet_b200.serve.DuplexEngine), per-tick latency p50 / p99 and the streams that sustain real time;
+  gpu_eager_baseline  the reference's eager arithmetic (the oracle port, same ATen calls) on THIS GPU: the same-box
+                      comparator BASELINE.md §4 names, for the codec pass and the LM step.
 """
 from __future__ import annotations
 
@@ -105,7 +115,7 @@ def cpu_sample(streams: int, frames: int, threads: int):
     """The reference's CPU path (oracle restatement, torch CPU fp32): streaming encode+decode."""
     import torch
     from oracle import mimi_oracle as O
-    from oracle import mimi_spec as S
+    from specs import mimi_spec as S
     torch.set_num_threads(threads)
     w = S.synthetic_weights(S.OFFICIAL, seed=41)
     x = S.synthetic_audio(streams, FRAME * (frames + 1), seed=0)
@@ -126,7 +136,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = best_cpu_threads()
-    streams, frames = 8, 4
+    streams, frames = 64, 2     # 64 streams: a quarter of the product arm's batch (torch CPU at 8 streams is overhead-bound)
     cpu_sample(streams, 1, threads)
     for _ in range(max(0, args.warmup - 1)):
         cpu_sample(streams, 1, threads)
@@ -153,7 +163,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from oracle import mimi_spec as S  # seeded synthetic weights / audio only (no compute from oracle/)
+    from specs import mimi_spec as S   # seeded synthetic weights / audio (neutral spec module; nothing from oracle/ here)
     from rstnet_b200 import _lib, ops
     from rstnet_b200.codec import MimiCodec
     from rstnet_b200.dist import reduce_timing
@@ -183,10 +193,11 @@ def run_ours(args):
 
     state = {"entered": False}
 
-    def step(resident: bool):
+    def step(resident: bool, cold: bool = True):
         """125 streaming frames for all streams: encode chunk -> decode tokens.  One streaming scope is
-        kept for the whole run (buffers + CUDA graphs are reused) and reset between passes."""
-        if state["entered"]:
+        kept for the whole run (buffers + CUDA graphs are reused) and reset between passes (cold = every pass starts
+        like a new 10 s stream; cold False keeps the state: the transformer rings stay full)."""
+        if state["entered"] and cold:
             m.reset_streaming()
         state["entered"] = True
         for i in range(FRAMES):
@@ -207,13 +218,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(resident: bool, steps: int):
+    def timed(resident: bool, steps: int, cold: bool = True):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _lib.launch_count()
         e0.record()
         for _ in range(steps):
-            step(resident)
+            step(resident, cold)
         e1.record()
         barrier()
         ms, _ = reduce_timing(e0.elapsed_time(e1), B * FRAMES * steps, device=dev)  # max over ranks
@@ -238,34 +249,50 @@ def run_ours(args):
     for _ in range(1):
         step(False)
     ms_e2e, _ = timed(False, args.steps)
+    # steady state: no reset between passes -> after the pass above the 250-token rings are full for every frame
+    step(True, cold=False)
+    ss_steps = max(1, min(args.steps, 4))
+    ms_ss, _ = timed(True, ss_steps, cold=False)
 
     frames_total = world * B * FRAMES * args.steps
     value = frames_total / (ms / 1e3)
     e2e_value = frames_total / (ms_e2e / 1e3)
+    ss_value = world * B * FRAMES * ss_steps / (ms_ss / 1e3)
 
     if rank == 0:
         roof = roofline_pass(m, x_dev, B, dev)
         cpu = None
+        extras = {}
         if world == 1:   # reported baseline: rank 0 at N = 1 only
             cpu_threads = best_cpu_threads()
-            cv, cdt = cpu_sample(8, 4, cpu_threads)
+            cv8, cdt8 = cpu_sample(8, 4, cpu_threads)
+            cv, cdt = cpu_sample(64, 2, cpu_threads)
             cpu = {"value": cv, "unit": UNIT, "cores": cpu_threads, "host_cores": os.cpu_count(), "kind": "port",
-                   "sample": f"8 streams x 4 frames streaming encode+decode, torch CPU fp32 oracle port ({cdt:.1f} s)"}
+                   "sample": f"64 streams x 2 frames streaming encode+decode, torch CPU fp32 oracle port ({cdt:.1f} s); "
+                             f"8 streams x 4 frames gives {cv8:.0f} frames/s"}
         lm = None
         if world == 1 and not args.no_lm:
+            def guarded(name, fn):
+                try:   # the codec headline must not be lost to a failure in a secondary measurement
+                    extras[name] = fn()
+                except Exception as e:
+                    extras[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                torch.cuda.empty_cache()
+            guarded("gpu_eager_codec", lambda: gpu_eager_codec_baseline(dev, B))
             m._stream_state = None
             m._engine = None
             torch.cuda.empty_cache()
-            try:
-                lm = lm_decode_bench(dev, steps=10, warmup=3)
-            except Exception as e:  # the codec headline must not be lost to an LM-side failure
-                lm = {"error": f"{type(e).__name__}: {e}"[:300]}
+            guarded("lm_decode", lambda: lm_decode_bench(dev, steps=10, warmup=3))
+            lm = extras.pop("lm_decode")
+            guarded("cfg4_infer", lambda: cfg4_infer_bench(dev, S))
+            guarded("cfg5_duplex", lambda: cfg5_duplex_bench(dev, S))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "streams_per_gpu": B, "frames_per_stream": FRAMES, "frame_samples": FRAME,
-                       "realtime_streams_per_gpu": value / world / 12.5, "cuda_graphs": True,
+                       "codec_only_realtime_streams_per_gpu": value / world / 12.5, "cuda_graphs": True,
+                       "start": "cold (every pass = new 10 s streams: the transformer rings fill from empty)",
                        "l2_policy": "inputs larger than L2 (246 MB audio + 320 MB weights per pass)",
                        "parallelism": f"dp{world}"},
             "clocks": clocks,
@@ -273,9 +300,20 @@ def run_ours(args):
                     "d2h_bytes_per_step": B * FRAMES * (FRAME * 4 + 8 * 8), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches_per_frame * FRAMES * args.steps),
             "roofline": roof,
+            "steady_state": {"value": ss_value, "unit": UNIT, "ms_per_step": ms_ss / ss_steps, "steps": ss_steps,
+                             "codec_only_realtime_streams_per_gpu": ss_value / world / 12.5,
+                             "note": "same pass without reset: every frame attends a full 250-token ring (long-running server)"},
             "lm_decode": lm,
             "cpu_baseline": cpu,
         }
+        if extras:
+            eager = extras.pop("gpu_eager_codec", None)
+            lm_eager = (lm or {}).pop("gpu_eager", None) if isinstance(lm, dict) else None
+            line["gpu_eager_baseline"] = {"codec": eager, "lm_decode": lm_eager,
+                                          "what": "the reference's eager arithmetic (oracle port = the same ATen calls) on this GPU"}
+            if isinstance(eager, dict) and eager.get("value"):
+                line["gpu_eager_baseline"]["codec_speedup"] = value / eager["value"]
+            line.update(extras)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -292,7 +330,7 @@ def roofline_pass(m, x_dev, B, dev):
     import torch
     from rstnet_b200 import ops
     peaks = _peaks()
-    rec = []
+    rec, rec_bytes = [], []
     orig = ops.TcGemm.run
 
     def timed_run(self):
@@ -301,6 +339,7 @@ def roofline_pass(m, x_dev, B, dev):
         orig(self)
         e1.record()
         rec.append((e0, e1, self.flops))
+        rec_bytes.append(self.bytes)
 
     m.use_cuda_graphs = False
     ops.TcGemm.run = timed_run  # plans bind `run` when they are built, so patch before the scope is created
@@ -310,6 +349,7 @@ def roofline_pass(m, x_dev, B, dev):
         m.decode(c)  # untimed warm frame
         torch.cuda.synchronize()
         rec.clear()
+        rec_bytes.clear()
         nframes = 3
         frame_ev = []
         for j in range(1, 1 + nframes):
@@ -330,8 +370,22 @@ def roofline_pass(m, x_dev, B, dev):
     flops = sum(f for _, _, f in rec)
     achieved = flops / (t_ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]
+    alg_bytes = sum(b for b in rec_bytes) / max(1, len(rec_bytes))     # per launch, like `traffic`
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r2_traffic.json")              # summary of the committed ncu pass (scripts/ncu_traffic.py)
+    if os.path.exists(tp):
+        try:
+            tj = json.load(open(tp))
+            k = tj["kernels"].get("gemm_tc_ts_kernel")
+            if k:
+                traffic, traffic_src = k["dram_bytes_per_launch"], tj.get("source")
+        except Exception:
+            pass
     return {"bound": "tensor", "kernel": "gemm_tc_ts_kernel (persistent tcgen05 kind::tf32 GEMM, A from TMEM, 3xTF32 split = fp32-equivalent; all conv/linear launches of a frame)",
-            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+            "traffic_source": traffic_src, "algorithmic_bytes_per_launch": alg_bytes,
+            "traffic_over_algorithmic": (traffic / alg_bytes) if traffic else None,
+            "frac_of_3xtf32_ceiling": achieved / (peak / 6.0),
             "peak_source": f"{peaks['source']} bf16 sustained (TF32 dense peak is half of it; 3xTF32 issues 3 MMAs per product, so the ceiling of this metric is peak/6)",
             "launches": len(rec) // nframes, "avg_launch_us": 1e3 * t_ms / max(1, len(rec)),
             "share_of_frame_time": t_ms / frame_ms, "eager_frame_ms": frame_ms / nframes,
@@ -383,6 +437,7 @@ def lm_decode_bench(dev, steps: int, warmup: int):
         for kv in st.kv:
             kv.normal_()
         st.offset.fill_(KV + 8)  # ring already wrapped: every step attends the full window
+        st.pos_host[:] = KV + 8
         g = torch.Generator(device=dev).manual_seed(0)
         seq = torch.randint(0, 2048, (B, 9, 1), device=dev, generator=g)
         seq[:, 0] = torch.randint(0, 128256, (B, 1), device=dev, generator=g)
@@ -440,9 +495,167 @@ def lm_decode_bench(dev, steps: int, warmup: int):
         d[0] += 1; d[1] += it[0].elapsed_time(it[1]); d[2] += it[2]
     out["gemm_by_shape_NK"] = {k: {"launches": v[0], "avg_us": 1e3 * v[1] / v[0], "gbs": v[2] / 1e9 / (v[1] * 1e-3)} for k, v in shapes.items()}
     m._state = None
+    m._packed = None
+    torch.cuda.empty_cache()
+    # same-box comparator: the reference's eager arithmetic on this GPU -- the oracle port executes the
+    # ATen calls of models/llama_streaming.py (F.linear, index_copy_ ring, boolean-mask SDPA over the whole ring, ...) in
+    # bf16 on the same weights, one launch per op, no CUDA graph (utils/compile.py's CUDAGraphed wraps only Moshi's LMGen)
+    try:
+        from oracle import lm_oracle as LO
+        ocfg = LO.LMConfig(context=KV, block_size=4096)
+        w = {k: v.detach() for k, v in m.state_dict().items()}
+        gs = LO.GPTStream(w, ocfg, B)
+        for r in gs.rings:
+            r.cache.normal_()
+            r.end_offset = KV + 8
+        gs.offset = KV + 8
+        with torch.no_grad():
+            LO.greedy_frame(gs, seq)
+            torch.cuda.synchronize()
+            e0.record()
+            n_e = 3
+            for _ in range(n_e):
+                LO.greedy_frame(gs, seq)
+            e1.record()
+            torch.cuda.synchronize()
+        ems = e0.elapsed_time(e1) / n_e
+        out["gpu_eager"] = {"ms_per_step": ems, "tokens_per_s": B * 9 / (ems * 1e-3), "speedup": ems / ms,
+                            "what": "oracle port (reference ATen calls) in bf16 on this GPU, greedy frame, eager"}
+        del gs, w
+    except Exception as e:
+        out["gpu_eager"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     del m
     torch.cuda.empty_cache()
     return out
+
+
+def gpu_eager_codec_baseline(dev, B):
+    """The reference's eager codec arithmetic on this GPU: the oracle's StreamingCodec (F.conv1d / conv_transpose1d /
+    F.linear / SDPA / cdist+argmin, one ATen call per op as MLLM_v2/modules does; PyTorch's default conv TF32 setting) with
+    the weights on the device, streaming, same batch as the headline.  Bounded sample: 1 warm-up + 5 timed frames."""
+    import torch
+    from oracle import mimi_oracle as O
+    from specs import mimi_spec as S
+    w = {k: v.to(dev) for k, v in S.synthetic_weights(S.OFFICIAL, seed=41).items()}
+    x = S.synthetic_audio(8, FRAME * 6, seed=3).repeat(B // 8, 1, 1).to(dev)
+    sc = O.StreamingCodec(w, B)
+    with torch.no_grad():
+        c = sc.encode(x[..., :FRAME]); sc.decode(c)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(1, 6):
+            c = sc.encode(x[..., i * FRAME:(i + 1) * FRAME]); sc.decode(c)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return {"value": B * 5 / (ms * 1e-3), "unit": UNIT, "ms_per_frame_batch": ms / 5,
+            "sample": f"{B} streams x 5 frames (cold start), torch eager fp32 (conv TF32 default: "
+                      f"{torch.backends.cudnn.allow_tf32})"}
+
+
+def _gpt7b(dev, context):
+    import torch
+    from rstnet_b200.lm import GPT, Config
+    cfg = Config(block_size=4096, n_layer=32, n_embd=4096, n_head=32, head_size=128, intermediate_size=11008,
+                 padded_vocab_size=152064, audio_card=2050, n_q=8, dep_q=8, codecformer_dim=1024, codecformer_heads=16,
+                 codecformer_layers=6, codecformer_dim_feedforward=4224, context=context)
+    return GPT(cfg, device=dev, dtype=torch.bfloat16).eval()
+
+
+def _mimi(dev, S):
+    from rstnet_b200.codec import MimiCodec
+    m = MimiCodec(encoder_rates=[8, 6, 5, 4], codebook_size=2048, codebook_dim=256, rvq_layers=8)
+    m.load_state_dict(S.synthetic_weights(S.OFFICIAL, seed=41), strict=True)
+    return m.to(dev).eval()
+
+
+def cfg4_infer_bench(dev, S, B: int = 32, prompt_frames: int = 50, gen_frames: int = 1000):
+    """BASELINE configs[3] (infer_no_streaming.py end to end): Mimi encode of the prompt audio -> InferenceImp (prefill of the
+    prompt, then `gen_frames` generated frames: temporal step + 8 depth steps + sampling each) -> reverse_delay -> Mimi
+    decode of everything generated; 7B random-init LM in bf16, B = 32 utterances, temp 0.8 / 0.7, top-k 30 / 25.
+    The prompt audio and the decoded waveforms cross PCIe inside the timed region."""
+    import torch
+    from rstnet_b200.infer import InferenceImp
+    codec = _mimi(dev, S)
+    lm = _gpt7b(dev, context=2048)
+    imp = InferenceImp(None, lm, "sampling", 0.7, 25, 0.8, 30, "TTS")
+    audio_host = S.synthetic_audio(8, FRAME * prompt_frames, seed=9).repeat(B // 8, 1, 1).pin_memory()
+    g = torch.Generator().manual_seed(4)
+    text = torch.randint(0, 128000, (B, prompt_frames), generator=g)
+
+    def run(n_gen):
+        t = {}
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        codes = codec.encode(audio_host.to(dev, non_blocking=True))                     # [B, 8, P]
+        seq = torch.full((B, 9, prompt_frames + n_gen), 128002, dtype=torch.int64, device=dev)   # text-empty = to generate
+        seq[:, 0, :prompt_frames] = text.to(dev)
+        seq[:, 1:, :prompt_frames] = codes
+        seq[:, 1:, prompt_frames:] = 0
+        ev[1].record()
+        out = imp.generate(seq)                                                         # [B, 8, n_gen - 1]
+        ev[2].record()
+        wav = codec.decode(out.clamp(max=2047))
+        wav_host = wav.cpu()
+        ev[3].record()
+        torch.cuda.synchronize()
+        return [ev[i].elapsed_time(ev[i + 1]) for i in range(3)], out, wav_host
+
+    run(8)                                   # warm-up: builds plans, captures the frame graphs
+    (t_enc, t_gen, t_dec), out, wav = run(gen_frames)
+    total = (t_enc + t_gen + t_dec) * 1e-3
+    res = {"workload": f"mimi_encode_{prompt_frames}f -> InferenceImp prefill+{gen_frames} frames -> mimi_decode, B={B}, 7B bf16 random init",
+           "seconds": {"encode_prompt": t_enc * 1e-3, "generate": t_gen * 1e-3, "decode": t_dec * 1e-3, "total": total},
+           "tokens_per_s": B * 9 * gen_frames / total, "frames_per_s": B * gen_frames / total,
+           "generate_ms_per_frame": t_gen / gen_frames, "audio_seconds_generated": B * (gen_frames - 1) * 0.08,
+           "realtime_factor": B * (gen_frames - 1) * 0.08 / total,
+           "h2d_bytes": int(audio_host.numel() * 4), "d2h_bytes": int(wav.numel() * 4), "codes_shape": list(out.shape)}
+    lm._state = None
+    del lm, codec, imp
+    return res
+
+
+def cfg5_duplex_bench(dev, S, ticks: int = 40):
+    """BASELINE configs[4] on ONE GPU: B concurrent dialogue streams through rstnet_b200.serve.DuplexEngine -- per 80 ms
+    tick: H2D of every stream's 1920-sample chunk, codec encode, one 7B LM frame (temporal + depth + sampling), codec
+    decode, D2H of tokens + PCM (the loop of moshi/server.py:108-144 for a batch).  Reports the wall-clock latency of a
+    tick (p50 / p99 over `ticks` ticks after warm-up) and which batch sizes stay under the 80 ms real-time budget.  The
+    7B MHA KV ring (context 2048, bf16) costs 1.07 GB per stream, which is what bounds streams per GPU."""
+    import torch
+    from rstnet_b200.serve import DuplexEngine, FrameScheduler
+    codec = _mimi(dev, S)
+    lm = _gpt7b(dev, context=2048)
+    res = {"tick_budget_ms": 80.0, "runs": []}
+    audio = S.synthetic_audio(8, FRAME * 8, seed=12)
+    for B in (64, 128):
+        try:
+            eng = DuplexEngine(codec, lm, B)
+            sch = FrameScheduler(eng, B)
+            for s in range(B):
+                sch.admit(s)
+            for tick in range(ticks + 6):
+                for s in range(B):
+                    sch.push(s, audio[s % 8, 0, (tick % 8) * FRAME:(tick % 8 + 1) * FRAME])
+                out = sch.tick()
+                assert len(out) == B
+            lat = sorted(eng.latencies_ms[6:])
+            p = lambda q: lat[min(len(lat) - 1, int(q * len(lat)))]
+            res["runs"].append({"streams": B, "tick_ms_p50": p(0.5), "tick_ms_p99": p(0.99), "tick_ms_max": lat[-1],
+                                "realtime": p(0.99) < 80.0, "frames_per_s": B / (p(0.5) * 1e-3),
+                                "headroom_x": 80.0 / p(0.5)})
+        except torch.cuda.OutOfMemoryError as e:
+            res["runs"].append({"streams": B, "error": "out of memory (KV rings)"})
+        lm._state = None
+        codec._stream_state = None
+        eng = sch = None
+        torch.cuda.empty_cache()
+    ok = [r["streams"] for r in res["runs"] if r.get("realtime")]
+    res["realtime_streams_per_gpu"] = max(ok) if ok else 0
+    res["note"] = ("codec + 7B LM per stream at an 80 ms cadence; the largest batch tried that keeps p99 < 80 ms "
+                   "(128 = one weight-streaming GEMM pass and ~137 GB of MHA KV rings)")
+    del lm, codec
+    return res
 
 
 def main():

@@ -107,9 +107,9 @@ def rope_pairs(q: torch.Tensor, k: torch.Tensor, offset: int, max_period: float)
     """Kyutai apply_rope, time_before_heads=False (R/modules/rope.py:11-68): rotation of
     (even, odd) pairs, angles computed on the fly in fp32. q,k: [B,H,T,D]."""
     B, H, T, D = q.shape
-    ds = torch.arange(D // 2, dtype=torch.float32)
+    ds = torch.arange(D // 2, dtype=torch.float32, device=q.device)
     freqs = torch.exp(ds * (-math.log(max_period) * 2 / D))
-    ts = (float(offset) + torch.arange(T, dtype=torch.float32)).view(1, -1, 1)
+    ts = (float(offset) + torch.arange(T, dtype=torch.float32, device=q.device)).view(1, -1, 1)
     rotr, roti = torch.cos(freqs * ts), torch.sin(freqs * ts)
     q2, k2 = q.view(B, H, T, D // 2, 2), k.view(B, H, T, D // 2, 2)
     qr, qi, kr, ki = q2[..., 0].float(), q2[..., 1].float(), k2[..., 0].float(), k2[..., 1].float()
@@ -122,18 +122,19 @@ class KVRing:
     """RingKVCache (R/modules/transformer.py:211-278): fixed-capacity ring written at
     (end_offset + t) % capacity; positions[-1] mark never-written slots."""
 
-    def __init__(self, batch: int, heads: int, dim: int, capacity: int, dtype=torch.float32):
+    def __init__(self, batch: int, heads: int, dim: int, capacity: int, dtype=torch.float32, device="cpu"):
         self.capacity = capacity
-        self.cache = torch.zeros(2, batch, heads, capacity, dim, dtype=dtype)
+        self.cache = torch.zeros(2, batch, heads, capacity, dim, dtype=dtype, device=device)
         self.end_offset = 0
 
     def complete(self, k: torch.Tensor, v: torch.Tensor):
         T = k.shape[2]
-        idx = (torch.arange(T) + self.end_offset) % self.capacity
+        dev = self.cache.device
+        idx = (torch.arange(T, device=dev) + self.end_offset) % self.capacity
         self.cache[0].index_copy_(2, idx, k)
         self.cache[1].index_copy_(2, idx, v)
         self.end_offset += T
-        slots = torch.arange(self.capacity)
+        slots = torch.arange(self.capacity, device=dev)
         end_index = self.end_offset % self.capacity
         delta = slots - end_index
         pos = torch.where(delta <= 0, self.end_offset + delta, self.end_offset + delta - self.capacity)
@@ -150,11 +151,11 @@ def mha(x: torch.Tensor, w: W, p: str, cfg: MimiConfig, offset: int, ring: Optio
     q, k, v = proj.view(B, T, 3, H, D // H).permute(2, 0, 3, 1, 4)
     q, k = rope_pairs(q, k, offset, cfg.max_period)
     if ring is None:
-        pos_k = torch.arange(T)
+        pos_k = torch.arange(T, device=x.device)
     else:
         k, v, pos_k = ring.complete(k, v)
     pos_k = pos_k.view(1, -1)
-    pos_q = offset + torch.arange(T).view(-1, 1)
+    pos_q = offset + torch.arange(T, device=x.device).view(-1, 1)
     delta = pos_q - pos_k
     bias = (pos_k >= 0) & (delta >= 0) & (delta < cfg.context)
     y = F.scaled_dot_product_attention(q, k, v, bias, dropout_p=0.0)
@@ -222,7 +223,7 @@ def rvq_encode(z: torch.Tensor, w: W, cfg: MimiConfig = OFFICIAL) -> torch.Tenso
     ResidualVectorQuantizer.encode (:134-147): rvq_first and rvq_rest each project the SAME
     latent with their own 1x1 input_proj. z [B,D,T] -> codes [B,n_q,T] int64."""
     if z.shape[-1] == 0:
-        return torch.empty((z.shape[0], cfg.n_q, 0), dtype=torch.int64)
+        return torch.empty((z.shape[0], cfg.n_q, 0), dtype=torch.int64, device=z.device)
     embs = codebooks(w, cfg)
     ns = cfg.n_q_semantic
     x1 = F.conv1d(z, w["quantizer.rvq_first.input_proj.weight"])
@@ -239,7 +240,7 @@ def rvq_decode(codes: torch.Tensor, w: W, cfg: MimiConfig = OFFICIAL) -> torch.T
     ns = cfg.n_q_semantic
 
     def group(cs, es, proj):
-        q = torch.zeros(())
+        q = torch.zeros((), device=cs.device)
         for lvl in range(cs.shape[1]):
             q = q + F.embedding(cs[:, lvl], es[lvl])
         return F.conv1d(q.permute(0, 2, 1), proj)
@@ -369,8 +370,9 @@ class StreamingCodec:
         idx += 1
         self.dec.append(("elu_conv", _ConvStream(w[f"decoder.model.{idx}.conv.conv.weight"], w[f"decoder.model.{idx}.conv.conv.bias"])))
         hd = D // cfg.num_heads
-        self.enc_rings = [KVRing(batch, cfg.num_heads, hd, cfg.context) for _ in range(cfg.num_layers)]
-        self.dec_rings = [KVRing(batch, cfg.num_heads, hd, cfg.context) for _ in range(cfg.num_layers)]
+        dev = w["downsample.conv.conv.conv.weight"].device   # weights on a GPU = the same ATen calls the reference eager makes there
+        self.enc_rings = [KVRing(batch, cfg.num_heads, hd, cfg.context, device=dev) for _ in range(cfg.num_layers)]
+        self.dec_rings = [KVRing(batch, cfg.num_heads, hd, cfg.context, device=dev) for _ in range(cfg.num_layers)]
         self.enc_offset = 0
         self.dec_offset = 0
 
@@ -389,6 +391,7 @@ class StreamingCodec:
             z = codec_transformer(z, self.w, "encoder_transformer", self.cfg, self.enc_offset, self.enc_rings)
             self.enc_offset += T
         z = self.down(z)
+        self.last_latent = z          # for rvq_margins: which frames may legitimately flip an index
         return rvq_encode(z, self.w, self.cfg)
 
     def decode(self, codes: torch.Tensor) -> torch.Tensor:

@@ -92,6 +92,11 @@ class TcGemm:
         d.act2 = act2
         self._keep = (A, W, W_lo, C_, bias, scale, R, C2)  # the plan embeds raw pointers
         self.flops = 2.0 * I_out * O_out * N * Ktot  # algorithmic (one fp32-equivalent product per MAC)
+        # algorithmic HBM bytes of the launch: every input element once, the weights once (hi and lo), the output(s) once
+        in_rows = min(a_o_extent, O_out * o_mul + (taps - 1) * max(tap_do, 0))
+        n_out = I_out * O_out * N
+        self.bytes = 4.0 * (a_c_extent * a_i_extent * in_rows + (2 if W_lo is not None else 1) * N * Ktot
+                            + n_out * (2 if C2 is not None else 1) + (n_out if R is not None else 0))
         self._h = C.c_void_p()
         _lib.check(_lib.lib().rstnet_tc_gemm_create(C.byref(d), C.byref(self._h)), "tc_gemm_create")
 
