@@ -226,7 +226,7 @@ __global__ void ring_attention_pair_kernel(const float* __restrict__ qkv, long l
 // 128-bit loads (two rows per instruction), the two half-warps accumulate alternate keys and are added at the end.
 // Ring slots advance incrementally (no per-key modulo).  At a 200-token context this kernel is 16 x 136 us of a
 // 256-stream frame in the one-row-per-lane form (launch list profiles/r1_codec_late_frame_launches_rowperlane_attn.csv).
-__global__ void ring_attention_pair64_kernel(const float* __restrict__ qkv, long long qbs, long long qts,
+__global__ void __launch_bounds__(128, 4) ring_attention_pair64_kernel(const float* __restrict__ qkv, long long qbs, long long qts,
                                              const float* __restrict__ kv, const long long* __restrict__ offset, int ostride,
                                              float* __restrict__ out, long long obs, long long ots, int B, int T, int H,
                                              int cap, int context, int linear) {
@@ -269,16 +269,26 @@ __global__ void ring_attention_pair64_kernel(const float* __restrict__ qkv, long
   for (long long p0 = lo0; p0 <= pos1; p0 += 32) {
     const int base = (int)(p0 % cap);
     // ---- scores of the 32 keys of the block: lane holds keys 4 it + grp, it = 0..7
+    // All 16 K loads of the block are issued before the first use (branch-free slot arithmetic keeps the unrolled loop
+    // one basic block): with a `while (slot >= cap)` wrap per key the compiler could keep only two loads in flight per
+    // warp and the kernel ran at memory LATENCY, not bandwidth (99 us per layer at a 200-token context, round 1).
     float s0[8], s1[8];
     {
-      int slot = base + grp;
-      while (slot >= cap) slot -= cap;
+      float4 kq[8][2];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        int slot = base + 4 * it + grp;               // base < cap and 4 it + grp < 32 <= cap (launcher: cap >= 32)
+        slot = slot >= cap ? slot - cap : slot;
+        const bool in = p0 + 4 * it + grp <= pos1;
+        const float* kr = Kb + (long long)(in ? slot : slot_last) * D + 8 * sub;
+        kq[it][0] = __ldg(reinterpret_cast<const float4*>(kr));
+        kq[it][1] = __ldg(reinterpret_cast<const float4*>(kr + 4));
+      }
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const long long p = p0 + 4 * it + grp;
         const bool in = p <= pos1;
-        const float* kr = Kb + (long long)(in ? slot : slot_last) * D + 8 * sub;
-        const float4 k0 = *reinterpret_cast<const float4*>(kr), k1 = *reinterpret_cast<const float4*>(kr + 4);
+        const float4 k0 = kq[it][0], k1 = kq[it][1];
         float d0 = qa[0] * k0.x, d1 = qb[0] * k0.x;
         d0 = fmaf(qa[1], k0.y, d0); d0 = fmaf(qa[2], k0.z, d0); d0 = fmaf(qa[3], k0.w, d0);
         d0 = fmaf(qa[4], k1.x, d0); d0 = fmaf(qa[5], k1.y, d0); d0 = fmaf(qa[6], k1.z, d0); d0 = fmaf(qa[7], k1.w, d0);
@@ -288,8 +298,6 @@ __global__ void ring_attention_pair64_kernel(const float* __restrict__ qkv, long
         for (int o = 1; o < 8; o <<= 1) { d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); }
         s0[it] = (p <= pos0) ? d0 * scale : -INFINITY;                 // p >= lo0 by construction
         s1[it] = (in && p >= lo1) ? d1 * scale : -INFINITY;
-        slot += 4;
-        while (slot >= cap) slot -= cap;
       }
     }
     float bm0 = s0[0], bm1 = s1[0];
@@ -310,20 +318,25 @@ __global__ void ring_attention_pair64_kernel(const float* __restrict__ qkv, long
     acc0.x *= c0; acc0.y *= c0; acc0.z *= c0; acc0.w *= c0;
     acc1.x *= c1; acc1.y *= c1; acc1.z *= c1; acc1.w *= c1;
     // ---- P.V: half-warp `half` takes keys 2 i + half
+    // keys past the pair's last position carry zero weights, so their V loads are redirected to the last valid row
+    // (finite values) instead of being skipped: all 16 loads go out together, no per-key branch
     const int nk = (int)min(32LL, pos1 - p0 + 1);
+    float4 vq[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int j = 2 * i + half;
+      int slot = base + j;
+      slot = slot >= cap ? slot - cap : slot;
+      vq[i] = __ldg(reinterpret_cast<const float4*>(Vb + (long long)(j < nk ? slot : slot_last) * D + 4 * vl));
+    }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       // key j = 2 i + half lives at register index j / 4 of the lanes of group j % 4
       const int src = (((2 * i) & 3) + half) << 3;
       const float w0 = __shfl_sync(0xffffffffu, s0[i >> 1], src), w1 = __shfl_sync(0xffffffffu, s1[i >> 1], src);
-      const int j = 2 * i + half;
-      if (j < nk) {
-        int slot = base + j;
-        while (slot >= cap) slot -= cap;
-        const float4 vv = *reinterpret_cast<const float4*>(Vb + (long long)slot * D + 4 * vl);
-        acc0.x = fmaf(w0, vv.x, acc0.x); acc0.y = fmaf(w0, vv.y, acc0.y); acc0.z = fmaf(w0, vv.z, acc0.z); acc0.w = fmaf(w0, vv.w, acc0.w);
-        acc1.x = fmaf(w1, vv.x, acc1.x); acc1.y = fmaf(w1, vv.y, acc1.y); acc1.z = fmaf(w1, vv.z, acc1.z); acc1.w = fmaf(w1, vv.w, acc1.w);
-      }
+      const float4 vv = vq[i];
+      acc0.x = fmaf(w0, vv.x, acc0.x); acc0.y = fmaf(w0, vv.y, acc0.y); acc0.z = fmaf(w0, vv.z, acc0.z); acc0.w = fmaf(w0, vv.w, acc0.w);
+      acc1.x = fmaf(w1, vv.x, acc1.x); acc1.y = fmaf(w1, vv.y, acc1.y); acc1.z = fmaf(w1, vv.z, acc1.z); acc1.w = fmaf(w1, vv.w, acc1.w);
     }
     m0 = m0n; m1 = m1n;
   }
@@ -366,7 +379,7 @@ extern "C" int rstnet_ring_attention_f32(const float* qkv, int64_t q_batch_strid
   const int warps = 4;
   const bool aligned16 = ((uintptr_t)qkv % 16) == 0 && ((uintptr_t)kv % 16) == 0 && ((uintptr_t)out % 16) == 0 && q_batch_stride % 4 == 0 &&
                          q_time_stride % 4 == 0 && o_batch_stride % 4 == 0 && o_time_stride % 4 == 0;
-  if (T >= 2 && D == 64 && aligned16) {
+  if (T >= 2 && D == 64 && aligned16 && cap >= 32) {   // the 64-dim kernel wraps a ring slot at most once per 32-key block
     const long long total = (long long)batch * ((T + 1) / 2) * H;
     ring_attention_pair64_kernel<<<ceil_div(total, warps), warps * 32, 0, (cudaStream_t)stream>>>(
         qkv, q_batch_stride, q_time_stride, kv, (const long long*)offset, ostride, out, o_batch_stride, o_time_stride, batch, T, H, cap,

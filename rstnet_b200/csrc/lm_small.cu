@@ -143,7 +143,7 @@ __global__ void rope_kv_append_bf16_kernel(const bf16* __restrict__ qkv, const b
 // Row r = tl*B + b queries stream b at position *offset + tl; all positions of the launch are already in the ring
 // (the caller guarantees no slot a query still needs has been overwritten: see GPT.forward_global's prefill path).
 template <int HS, int G>
-__global__ void __launch_bounds__(256) ring_decode_attention_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kv,
+__global__ void __launch_bounds__(256, (G == 1 ? 3 : 2)) ring_decode_attention_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kv,
                                                                     const long long* __restrict__ offset, bf16* __restrict__ out,
                                                                     int ostride, int B, int nh, int n_kv, int cap, int context,
                                                                     float scale) {
