@@ -280,6 +280,31 @@ int rstnet_lm_silu_mul_bf16(const void* ab, void* out, int32_t M, int32_t I, rst
  * on the last step; 0: non-streaming form (forward_local, :694-725; KVCacheResult.from_kv keeps every key). */
 int rstnet_lm_depth_attention_bf16(const void* qkv, void* kvd, void* out, int32_t B, int32_t H, int32_t hd, int32_t cap,
                                    int32_t step, int32_t ring_quirk, rstnet_stream_t stream);
+/* ---- the depth transformer of a frame as ONE persistent (cooperative) kernel: steps [k_begin, k_end) of
+ * GPT.forward_codecformer (llama_streaming.py:727-749; per-step weights modules/transformer.py:155-179, 518-577; gating
+ * modules/gating.py:12-21), each = codecformer_in[k](transformer_out) + embedding of the step's input token, L layers
+ * (RMSNorm-f32, per-step in/out projections, attention over the <= dep_q keys of this frame, SiLU gating), audio_linears[k]
+ * -> logits[k][M][card], and (do_sample) sample_token_audio on the device: tokens[m][k + 1] feeds step k + 1.
+ * tokens[m][k] is the INPUT token of step k (column 0: the text token).  All buffers are the caller's; `barrier` is two
+ * uint32 words (arrival counter, zeroed by run; sticky error word: bit 0 token id outside its table, bit 2 barrier
+ * watchdog).  w_gin[l*Q + k]: gating linear_in with its rows interleaved in 8-row groups [a_8u..8u+7; b_8u..8u+7] and the
+ * hidden width zero-padded to Hp (a multiple of 128); w_gout[l*Q + k]: linear_out [D][Hp].  Requires M <= 128,
+ * D, E, Hp multiples of 128, D <= 2048.  step0_embedding (optional, [M][D]) replaces the token lookup of step 0
+ * (forward_local passes features there, llama_streaming.py:700-705); ring_quirk as in rstnet_lm_depth_attention_bf16. */
+typedef struct rstnet_depth_plan rstnet_depth_plan;
+typedef struct {
+  int32_t M, D, E, Hp, H, hd, Q, L, card, tok_stride;
+  const void* tout; void* x; void* qkv; void* att; void* dh; void* logits; void* dkv; float* ss_part; int64_t* tokens; void* barrier;
+  const void* w_in[8]; const void* emb[8]; int64_t emb_rows[8]; const void* w_head[8];
+  const void* w_qkv[8]; const void* w_out[8]; const void* a1[8]; const void* a2[8];
+  const void* w_gin[64]; const void* w_gout[64];
+} rstnet_depth_frame_desc;
+int rstnet_lm_depth_frame_create(const rstnet_depth_frame_desc* desc, rstnet_depth_plan** plan);
+int rstnet_lm_depth_frame_run(const rstnet_depth_plan* plan, int32_t k_begin, int32_t k_end, int32_t ring_quirk, int32_t do_sample,
+                              int32_t top_k, float temp, uint32_t seed, const int64_t* frame_counter, const int32_t* n_valid,
+                              const void* step0_embedding, rstnet_stream_t stream);
+void rstnet_lm_depth_frame_destroy(rstnet_depth_plan* plan);
+
 /* ---- sample_token / sample_token_audio[_2048] (utils/sampling.py:85-154): ids restricted to [0, n_valid);
  * top_k == 0 -> argmax (first maximum; use_sampling False); 1 <= top_k <= 1024 -> top-k + temperature +
  * exponential-noise multinomial (sample_top_k, :49-60); top_k < 0 -> temperature multinomial over all n_valid ids
