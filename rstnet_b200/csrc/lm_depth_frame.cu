@@ -96,11 +96,17 @@ __device__ __forceinline__ void grid_barrier(const DepthFrameParams& p, unsigned
     __threadfence();
     atomicAdd(p.barrier, 1u);
     const long long t0 = clock64();
+    unsigned int spins = 0;
     while (true) {
       unsigned int v;
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.barrier) : "memory");
       if (v >= target) break;
-      if (clock64() - t0 > 4000000000LL) { atomicOr(p.err, 4u); break; }   // ~2 s
+      if ((++spins & 1023u) == 0) {
+        unsigned int e;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(p.err) : "memory");
+        if (e & 4u) break;                                                    // somebody already gave up: do not wait again
+        if (clock64() - t0 > 2000000000LL) { atomicOr(p.err, 4u); break; }   // ~1 s
+      }
     }
     __threadfence();
   }
