@@ -266,6 +266,7 @@ __global__ void __launch_bounds__(128, 4) ring_attention_pair64_kernel(const flo
   float m0 = -INFINITY, l0 = 0.f, m1 = -INFINITY, l1 = 0.f;
   float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
   const int slot_last = (int)(pos1 % cap);
+  const bool small_ring = cap < 32;        // uniform: short non-streaming clips (cap == T) and test rings
   for (long long p0 = lo0; p0 <= pos1; p0 += 32) {
     const int base = (int)(p0 % cap);
     // ---- scores of the 32 keys of the block: lane holds keys 4 it + grp, it = 0..7
@@ -277,8 +278,8 @@ __global__ void __launch_bounds__(128, 4) ring_attention_pair64_kernel(const flo
       float4 kq[8][2];
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
-        int slot = base + 4 * it + grp;               // base < cap and 4 it + grp < 32 <= cap (launcher: cap >= 32)
-        slot = slot >= cap ? slot - cap : slot;
+        int slot = base + 4 * it + grp;               // base < cap and 4 it + grp < 32: one wrap unless the ring is tiny
+        slot = small_ring ? slot % cap : (slot >= cap ? slot - cap : slot);
         const bool in = p0 + 4 * it + grp <= pos1;
         const float* kr = Kb + (long long)(in ? slot : slot_last) * D + 8 * sub;
         kq[it][0] = __ldg(reinterpret_cast<const float4*>(kr));
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(128, 4) ring_attention_pair64_kernel(const flo
     for (int i = 0; i < 16; ++i) {
       const int j = 2 * i + half;
       int slot = base + j;
-      slot = slot >= cap ? slot - cap : slot;
+      slot = small_ring ? slot % cap : (slot >= cap ? slot - cap : slot);
       vq[i] = __ldg(reinterpret_cast<const float4*>(Vb + (long long)(j < nk ? slot : slot_last) * D + 4 * vl));
     }
 #pragma unroll
@@ -379,7 +380,7 @@ extern "C" int rstnet_ring_attention_f32(const float* qkv, int64_t q_batch_strid
   const int warps = 4;
   const bool aligned16 = ((uintptr_t)qkv % 16) == 0 && ((uintptr_t)kv % 16) == 0 && ((uintptr_t)out % 16) == 0 && q_batch_stride % 4 == 0 &&
                          q_time_stride % 4 == 0 && o_batch_stride % 4 == 0 && o_time_stride % 4 == 0;
-  if (T >= 2 && D == 64 && aligned16 && cap >= 32) {   // the 64-dim kernel wraps a ring slot at most once per 32-key block
+  if (T >= 2 && D == 64 && aligned16) {
     const long long total = (long long)batch * ((T + 1) / 2) * H;
     ring_attention_pair64_kernel<<<ceil_div(total, warps), warps * 32, 0, (cudaStream_t)stream>>>(
         qkv, q_batch_stride, q_time_stride, kv, (const long long*)offset, ostride, out, o_batch_stride, o_time_stride, batch, T, H, cap,

@@ -137,13 +137,33 @@ __device__ void gemm_phase(const DepthFrameParams& p, uint8_t* smem, const bf16*
   const uint32_t smem_base = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
 
   if (norm_alpha) {
+    // r[m] from the producer's per-block sums of squares.  The nb partials of a row are spread over `nsub` threads, each
+    // issuing its loads in independent batches of 8 (a plain dependent loop cost nb L2 round trips: 40 us per phase),
+    // then added in a fixed order.
     const int nb = K / 16;
-    for (int m = tid; m < Mpad; m += DF_THREADS) {
-      float ss = 0.f;
-      if (m < M)
-        for (int j = 0; j < nb; ++j) ss += __ldcg(p.ss_part + (long long)j * M + m);
-      s_r[m] = rsqrtf(1e-8f + ss / (float)K);
+    const int mc = Mpad <= 64 ? 64 : 128, nsub = DF_THREADS / mc;
+    const int m = tid % mc, q = tid / mc;
+    float ss = 0.f;
+    if (m < M) {
+      for (int j0 = q; j0 < nb; j0 += 8 * nsub) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int j = j0 + e * nsub;
+          v[e] = j < nb ? __ldcg(p.ss_part + (long long)j * M + m) : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ss += v[e];
+      }
     }
+    s_alpha[q * 128 + m] = ss;            // scratch: [nsub][128] partial sums (the buffer holds max(D, 512) floats)
+    __syncthreads();
+    if (tid < Mpad) {
+      float tot = 0.f;
+      for (int qq = 0; qq < nsub; ++qq) tot += s_alpha[qq * 128 + tid];
+      s_r[tid] = rsqrtf(1e-8f + tot / (float)K);
+    }
+    __syncthreads();
     for (int k = tid; k < K; k += DF_THREADS) s_alpha[k] = b2f(norm_alpha[k]);
   }
   __syncthreads();
@@ -410,7 +430,8 @@ extern "C" int rstnet_lm_depth_frame_create(const rstnet_depth_frame_desc* d, rs
   p.top_k = 0; p.temp = 1.f; p.seed = 0; p.frame_counter = nullptr;
   for (int k = 0; k < DF_MAXQ; ++k) p.n_valid[k] = d->card;
   const int Mpad = (d->M + 7) & ~7;
-  pl->smem = (size_t)DF_STAGES * (Mpad * DF_PITCH + DF_MAXU * 16 * DF_PITCH) + 128 * sizeof(float) + (size_t)d->D * sizeof(float);
+  pl->smem = (size_t)DF_STAGES * (Mpad * DF_PITCH + DF_MAXU * 16 * DF_PITCH) + 128 * sizeof(float) +
+             (size_t)(d->D > 512 ? d->D : 512) * sizeof(float);      // s_alpha doubles as a [4][128] reduction scratch
   static unsigned long long attr = 0;
   smem_optin(depth_frame_kernel, 200 * 1024, attr);
   RSTNET_REQUIRE(pl->smem <= 200 * 1024, "depth_frame_create: shared memory budget exceeded");
