@@ -304,6 +304,8 @@ int rstnet_lm_depth_frame_run(const rstnet_depth_plan* plan, int32_t k_begin, in
                               int32_t top_k, float temp, uint32_t seed, const int64_t* frame_counter, const int32_t* n_valid,
                               const void* step0_embedding, rstnet_stream_t stream);
 void rstnet_lm_depth_frame_destroy(rstnet_depth_plan* plan);
+/* profiling aid: CTA 0 writes clock64 stamps (start, then after every phase and after every barrier) to trace[>= 1024] */
+void rstnet_lm_depth_frame_set_trace(rstnet_depth_plan* plan, int64_t* trace);
 
 /* ---- sample_token / sample_token_audio[_2048] (utils/sampling.py:85-154): ids restricted to [0, n_valid);
  * top_k == 0 -> argmax (first maximum; use_sampling False); 1 <= top_k <= 1024 -> top-k + temperature +

@@ -24,7 +24,7 @@ SYMBOLS = [
     "rstnet_skinny_gemm_workspace", "rstnet_skinny_gemm_create", "rstnet_skinny_gemm_create_fused", "rstnet_skinny_gemm_run", "rstnet_skinny_gemm_destroy",
     "rstnet_lm_embed_sum_bf16", "rstnet_lm_embed_rows_bf16", "rstnet_lm_rms_norm_bf16", "rstnet_lm_rope_kv_append_bf16",
     "rstnet_lm_ring_decode_attention_bf16", "rstnet_lm_silu_mul_bf16", "rstnet_lm_depth_attention_bf16", "rstnet_lm_sample_bf16",
-    "rstnet_lm_depth_frame_create", "rstnet_lm_depth_frame_run", "rstnet_lm_depth_frame_destroy",
+    "rstnet_lm_depth_frame_create", "rstnet_lm_depth_frame_run", "rstnet_lm_depth_frame_destroy", "rstnet_lm_depth_frame_set_trace",
 ]
 
 
@@ -138,6 +138,8 @@ def lib() -> C.CDLL:
     L.rstnet_lm_depth_frame_run.argtypes = [vp, i32, i32, i32, i32, i32, f32, C.c_uint32, vp, vp, vp, vp]
     L.rstnet_lm_depth_frame_destroy.argtypes = [vp]
     L.rstnet_lm_depth_frame_destroy.restype = None
+    L.rstnet_lm_depth_frame_set_trace.argtypes = [vp, vp]
+    L.rstnet_lm_depth_frame_set_trace.restype = None
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("rstnet_version",):

@@ -31,9 +31,11 @@ __device__ __forceinline__ bf16 f2b(float v) { return __float2bfloat16(v); }
 constexpr int DF_THREADS = 256;
 constexpr int DF_KC = 128;                // K elements per pipeline stage
 constexpr int DF_PITCH = DF_KC * 2 + 16;  // shared-memory row pitch in bytes: 8 consecutive rows hit distinct banks (ldmatrix)
-constexpr int DF_STAGES = 3;
+// pipeline depth: per chunk a CTA has only ~30 KB in flight, and a chunk costs a full DRAM round trip (~1 us measured with
+// 3 stages: the phases ran at memory latency); 6 stages for <= 64 streams, 4 for <= 128 (shared-memory budget)
 constexpr int DF_MAXU = 3;                // 16-row weight blocks per CTA per round
 constexpr int DF_MAXQ = 8, DF_MAXL = 8;
+constexpr int DF_SMEM_MAX = 201 * 1024;   // dynamic; the sampler's static arrays (25 KB) come on top: 227 KB per CTA in all
 
 struct DepthFrameParams {
   int M, D, E, Hp, H, hd, Q, L, card;
@@ -62,7 +64,13 @@ struct DepthFrameParams {
   const bf16* w_gout[DF_MAXL][DF_MAXQ];  // gating linear_out, K padded    [D][Hp]
   const bf16* w_head[DF_MAXQ];        // audio_linears[k]              [card][D]
   int top_k; float temp; unsigned int seed; const long long* frame_counter; int n_valid[DF_MAXQ];
+  long long* trace;      // profiling aid (RSTNET_DEPTH_TRACE): CTA 0 stamps clock64 after every phase and every barrier
 };
+
+#define DF_STAMP()                                                      \
+  do {                                                                  \
+    if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[tr++] = clock64(); \
+  } while (0)
 
 __device__ __forceinline__ void cp_async16_cg(uint32_t smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc));
@@ -121,16 +129,45 @@ enum DfEpi : int { EPI_STORE = 0, EPI_RES = 1, EPI_IN = 2, EPI_SILU = 3 };
 //   EPI_RES:   out = bf16(bf16(acc) + out)  + ss_part             (out-proj / gating-out residual adds)
 //   EPI_IN:    out = bf16(bf16(acc) + emb[token[m]])  + ss_part   (step input: codecformer_in + token embedding)
 //   EPI_SILU:  rows [a(8); b(8)] per block: out[m][8u+g] = bf16(bf16(silu(bf16 a)) * bf16 b)
-template <int EPI>
+// issue the weight chunks 0 .. STAGES-2 of a phase's first round (one cp.async group each) -- they do not depend on the
+// previous phase, so they are put in flight BEFORE the grid barrier that precedes the phase
+template <int STAGES>
+__device__ void prefetch_weights(const DepthFrameParams& p, uint8_t* smem, const bf16* __restrict__ W, int N, int K) {
+  const int Mpad = (p.M + 7) & ~7;
+  const int x_bytes = Mpad * DF_PITCH, stage_bytes = x_bytes + DF_MAXU * 16 * DF_PITCH;
+  const uint32_t smem_base = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  const int nunits = (N + 15) / 16, nchunks = K / DF_KC;
+  int U = 0;
+  int units[DF_MAXU];
+#pragma unroll
+  for (int i = 0; i < DF_MAXU; ++i) {
+    units[i] = blockIdx.x + i * gridDim.x;
+    if (units[i] < nunits) U = i + 1;
+  }
+  for (int c = 0; c < STAGES - 1; ++c) {
+    if (c < nchunks) {
+      const uint32_t ws = smem_base + (c % STAGES) * stage_bytes + x_bytes;
+      for (int i = threadIdx.x; i < U * 256; i += DF_THREADS) {
+        const int ui = i >> 8, r = (i >> 4) & 15, piece = i & 15;
+        int n = units[ui] * 16 + r;
+        n = n < N ? n : N - 1;
+        cp_async16_cg(ws + (ui * 16 + r) * DF_PITCH + piece * 16, W + (long long)n * K + c * DF_KC + piece * 8);
+      }
+    }
+    cp_async_commit();
+  }
+}
+
+template <int EPI, int STAGES>
 __device__ void gemm_phase(const DepthFrameParams& p, uint8_t* smem, const bf16* __restrict__ W, int N, int K,
                            const bf16* __restrict__ X, int ldx, const bf16* __restrict__ norm_alpha, bf16* __restrict__ out, int ldo,
-                           int step_k) {
+                           int step_k, bool w_prefetched) {
   const int M = p.M;
   const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
   const int Mpad = (M + 7) & ~7;
   const int x_bytes = Mpad * DF_PITCH;
   const int stage_bytes = x_bytes + DF_MAXU * 16 * DF_PITCH;
-  float* s_r = reinterpret_cast<float*>(smem + DF_STAGES * stage_bytes);   // [128]
+  float* s_r = reinterpret_cast<float*>(smem + STAGES * stage_bytes);   // [128]
   float* s_alpha = s_r + 128;                                                // [K] (norm phases have K == D)
   const int nunits = (N + 15) / 16;
   const int nchunks = K / DF_KC;
@@ -176,8 +213,8 @@ __device__ void gemm_phase(const DepthFrameParams& p, uint8_t* smem, const bf16*
       units[i] = u0 + i * gridDim.x;
       if (units[i] < nunits) U = i + 1;
     }
-    auto issue = [&](int c) {
-      const int s = c % DF_STAGES;
+    auto issue = [&](int c, bool with_w) {
+      const int s = c % STAGES;
       const uint32_t xs = smem_base + s * stage_bytes, ws = xs + x_bytes;
       const int k0 = c * DF_KC;
       for (int i = tid; i < Mpad * 16; i += DF_THREADS) {       // 16 x 16-byte pieces per 128-element row
@@ -185,14 +222,17 @@ __device__ void gemm_phase(const DepthFrameParams& p, uint8_t* smem, const bf16*
         const int mm = m < M ? m : M - 1;                       // padding rows repeat the last stream (never stored)
         cp_async16_cg(xs + m * DF_PITCH + piece * 16, X + (long long)mm * ldx + k0 + piece * 8);
       }
-      for (int i = tid; i < U * 256; i += DF_THREADS) {
-        const int ui = i >> 8, r = (i >> 4) & 15, piece = i & 15;
-        int n = units[ui] * 16 + r;
-        n = n < N ? n : N - 1;
-        cp_async16_cg(ws + (ui * 16 + r) * DF_PITCH + piece * 16, W + (long long)n * K + k0 + piece * 8);
+      if (with_w) {
+        for (int i = tid; i < U * 256; i += DF_THREADS) {
+          const int ui = i >> 8, r = (i >> 4) & 15, piece = i & 15;
+          int n = units[ui] * 16 + r;
+          n = n < N ? n : N - 1;
+          cp_async16_cg(ws + (ui * 16 + r) * DF_PITCH + piece * 16, W + (long long)n * K + k0 + piece * 8);
+        }
       }
       cp_async_commit();
     };
+    const bool pre = w_prefetched && u0 == (int)blockIdx.x;    // the first round's first weight chunks are already in flight
     float acc[DF_MAXU][2][4];
 #pragma unroll
     for (int i = 0; i < DF_MAXU; ++i)
@@ -201,14 +241,14 @@ __device__ void gemm_phase(const DepthFrameParams& p, uint8_t* smem, const bf16*
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
 
-    for (int c = 0; c < DF_STAGES - 1; ++c) {
-      if (c < nchunks) issue(c); else cp_async_commit();
+    for (int c = 0; c < STAGES - 1; ++c) {
+      if (c < nchunks) issue(c, !pre); else cp_async_commit();
     }
     for (int c = 0; c < nchunks; ++c) {
-      cp_async_wait<DF_STAGES - 2>();
+      cp_async_wait<STAGES - 2>();
       __syncthreads();                       // chunk c landed for everyone; everyone is done with chunk c - 1's slot
-      if (c + DF_STAGES - 1 < nchunks) issue(c + DF_STAGES - 1); else cp_async_commit();
-      const int s = c % DF_STAGES;
+      if (c + STAGES - 1 < nchunks) issue(c + STAGES - 1, true); else cp_async_commit();
+      const int s = c % STAGES;
       const uint32_t xs = smem_base + s * stage_bytes, ws = xs + x_bytes;
       const int k0 = c * DF_KC;
 #pragma unroll
@@ -357,28 +397,42 @@ __device__ void attention_phase(const DepthFrameParams& p, int layer, int step) 
   }
 }
 
+template <int STAGES>
 __global__ void __launch_bounds__(DF_THREADS, 1) depth_frame_kernel(const __grid_constant__ DepthFrameParams p) {
   extern __shared__ __align__(128) uint8_t df_smem[];
   unsigned int target = 0;
+  int tr = 0;
   const int D = p.D;
+  DF_STAMP();
+  bool pf = false;    // the next GEMM phase's first weight chunks are already in flight
   for (int k = p.k_begin; k < p.k_end; ++k) {
-    gemm_phase<EPI_IN>(p, df_smem, p.w_in[k], D, p.E, p.tout, p.E, nullptr, p.x, D, k);
-    grid_barrier(p, target);
+    gemm_phase<EPI_IN, STAGES>(p, df_smem, p.w_in[k], D, p.E, p.tout, p.E, nullptr, p.x, D, k, pf);
+    prefetch_weights<STAGES>(p, df_smem, p.w_qkv[0] + (long long)k * 3 * D * D, 3 * D, D);
+    DF_STAMP(); grid_barrier(p, target); DF_STAMP();
     for (int l = 0; l < p.L; ++l) {
-      gemm_phase<EPI_STORE>(p, df_smem, p.w_qkv[l] + (long long)k * 3 * D * D, 3 * D, D, p.x, D, p.a1[l], p.qkv, 3 * D, k);
-      grid_barrier(p, target);
+      gemm_phase<EPI_STORE, STAGES>(p, df_smem, p.w_qkv[l] + (long long)k * 3 * D * D, 3 * D, D, p.x, D, p.a1[l], p.qkv, 3 * D, k, true);
+      prefetch_weights<STAGES>(p, df_smem, p.w_out[l] + (long long)k * D * D, D, D);      // in flight across the attention phase
+      DF_STAMP(); grid_barrier(p, target); DF_STAMP();
       attention_phase(p, l, k);
-      grid_barrier(p, target);
-      gemm_phase<EPI_RES>(p, df_smem, p.w_out[l] + (long long)k * D * D, D, D, p.att, D, nullptr, p.x, D, k);
-      grid_barrier(p, target);
-      gemm_phase<EPI_SILU>(p, df_smem, p.w_gin[l][k], 2 * p.Hp, D, p.x, D, p.a2[l], p.dh, p.Hp, k);
-      grid_barrier(p, target);
-      gemm_phase<EPI_RES>(p, df_smem, p.w_gout[l][k], D, p.Hp, p.dh, p.Hp, nullptr, p.x, D, k);
-      grid_barrier(p, target);
+      DF_STAMP(); grid_barrier(p, target); DF_STAMP();
+      gemm_phase<EPI_RES, STAGES>(p, df_smem, p.w_out[l] + (long long)k * D * D, D, D, p.att, D, nullptr, p.x, D, k, true);
+      prefetch_weights<STAGES>(p, df_smem, p.w_gin[l][k], 2 * p.Hp, D);
+      DF_STAMP(); grid_barrier(p, target); DF_STAMP();
+      gemm_phase<EPI_SILU, STAGES>(p, df_smem, p.w_gin[l][k], 2 * p.Hp, D, p.x, D, p.a2[l], p.dh, p.Hp, k, true);
+      prefetch_weights<STAGES>(p, df_smem, p.w_gout[l][k], D, p.Hp);
+      DF_STAMP(); grid_barrier(p, target); DF_STAMP();
+      gemm_phase<EPI_RES, STAGES>(p, df_smem, p.w_gout[l][k], D, p.Hp, p.dh, p.Hp, nullptr, p.x, D, k, true);
+      if (l + 1 < p.L) prefetch_weights<STAGES>(p, df_smem, p.w_qkv[l + 1] + (long long)k * 3 * D * D, 3 * D, D);
+      else prefetch_weights<STAGES>(p, df_smem, p.w_head[k], p.card, D);
+      DF_STAMP(); grid_barrier(p, target); DF_STAMP();
     }
     bf16* lg = p.logits + (long long)k * p.M * p.card;
-    gemm_phase<EPI_STORE>(p, df_smem, p.w_head[k], p.card, D, p.x, D, nullptr, lg, p.card, k);
+    gemm_phase<EPI_STORE, STAGES>(p, df_smem, p.w_head[k], p.card, D, p.x, D, nullptr, lg, p.card, k, true);
+    pf = false;
+    if (k + 1 < p.k_end) { prefetch_weights<STAGES>(p, df_smem, p.w_in[k + 1], D, p.E); pf = true; }
+    DF_STAMP();
     if (p.do_sample || k + 1 < p.k_end) grid_barrier(p, target);     // logits complete; nobody still reads x
+    DF_STAMP();
     if (p.do_sample) {
       const unsigned int stepc = p.frame_counter ? (unsigned int)(*p.frame_counter) : 0u;
       for (int m = blockIdx.x; m < p.M; m += gridDim.x)
@@ -387,6 +441,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) depth_frame_kernel(const __grid
       if (k + 1 < p.k_end) grid_barrier(p, target);                  // the sampled tokens feed the next step's embedding
     }
   }
+  cp_async_wait<0>();
 }
 
 }  // namespace rstnet
@@ -395,8 +450,12 @@ using namespace rstnet;
 struct rstnet_depth_plan {
   DepthFrameParams p;
   int grid;
+  int stages;
   size_t smem;
+  long long* trace = nullptr;
 };
+
+extern "C" void rstnet_lm_depth_frame_set_trace(rstnet_depth_plan* pl, int64_t* trace) { pl->trace = (long long*)trace; }
 
 extern "C" int rstnet_lm_depth_frame_create(const rstnet_depth_frame_desc* d, rstnet_depth_plan** out) {
   RSTNET_REQUIRE(d && out, "depth_frame_create: null pointer");
@@ -427,18 +486,20 @@ extern "C" int rstnet_lm_depth_frame_create(const rstnet_depth_frame_desc* d, rs
       RSTNET_REQUIRE(p.w_gin[l][k] && p.w_gout[l][k], "depth_frame_create: null gating weight (layer %d step %d)", l, k);
     }
   }
-  p.top_k = 0; p.temp = 1.f; p.seed = 0; p.frame_counter = nullptr;
+  p.top_k = 0; p.temp = 1.f; p.seed = 0; p.frame_counter = nullptr; p.trace = nullptr;
   for (int k = 0; k < DF_MAXQ; ++k) p.n_valid[k] = d->card;
   const int Mpad = (d->M + 7) & ~7;
-  pl->smem = (size_t)DF_STAGES * (Mpad * DF_PITCH + DF_MAXU * 16 * DF_PITCH) + 128 * sizeof(float) +
+  pl->stages = d->M <= 64 ? 6 : 4;
+  pl->smem = (size_t)pl->stages * (Mpad * DF_PITCH + DF_MAXU * 16 * DF_PITCH) + 128 * sizeof(float) +
              (size_t)(d->D > 512 ? d->D : 512) * sizeof(float);      // s_alpha doubles as a [4][128] reduction scratch
-  static unsigned long long attr = 0;
-  smem_optin(depth_frame_kernel, 200 * 1024, attr);
-  RSTNET_REQUIRE(pl->smem <= 200 * 1024, "depth_frame_create: shared memory budget exceeded");
+  RSTNET_REQUIRE(pl->smem <= DF_SMEM_MAX, "depth_frame_create: shared memory budget exceeded");
+  static unsigned long long attr6 = 0, attr4 = 0;
+  if (pl->stages == 6) smem_optin(depth_frame_kernel<6>, DF_SMEM_MAX, attr6); else smem_optin(depth_frame_kernel<4>, DF_SMEM_MAX, attr4);
   int dev = 0, sms = 0, per_sm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, depth_frame_kernel, DF_THREADS, pl->smem);
+  if (pl->stages == 6) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, depth_frame_kernel<6>, DF_THREADS, pl->smem);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, depth_frame_kernel<4>, DF_THREADS, pl->smem);
   if (per_sm < 1) { delete pl; set_error("depth_frame_create: the kernel does not fit on an SM"); return 3; }
   pl->grid = sms;
   *out = pl;
@@ -451,12 +512,13 @@ extern "C" int rstnet_lm_depth_frame_run(const rstnet_depth_plan* pl, int32_t k_
   RSTNET_REQUIRE(pl != nullptr, "depth_frame_run: null plan");
   RSTNET_REQUIRE(k_begin >= 0 && k_begin < k_end && k_end <= pl->p.Q, "depth_frame_run: bad step range [%d, %d)", k_begin, k_end);
   RSTNET_REQUIRE(!do_sample || (top_k <= SAMPLE_CAND && (top_k == 0 || temp > 0.f)), "depth_frame_run: bad sampling parameters");
-  static unsigned long long attr = 0;
-  smem_optin(depth_frame_kernel, 200 * 1024, attr);      // per device (create may have run with another device current)
+  static unsigned long long attr6 = 0, attr4 = 0;           // per device (create may have run with another device current)
+  if (pl->stages == 6) smem_optin(depth_frame_kernel<6>, DF_SMEM_MAX, attr6); else smem_optin(depth_frame_kernel<4>, DF_SMEM_MAX, attr4);
   DepthFrameParams p = pl->p;
   p.k_begin = k_begin; p.k_end = k_end; p.ring_quirk = ring_quirk; p.do_sample = do_sample;
   p.top_k = top_k; p.temp = temp; p.seed = seed; p.frame_counter = (const long long*)frame_counter;
   p.emb0_rows = (const bf16*)step0_embedding;
+  p.trace = pl->trace;
   for (int k = 0; k < pl->p.Q; ++k) {
     int nv = n_valid ? n_valid[k] : p.card;
     if (nv <= 0 || nv > p.card) nv = p.card;
@@ -466,7 +528,8 @@ extern "C" int rstnet_lm_depth_frame_run(const rstnet_depth_plan* pl, int32_t k_
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(p.barrier, 0, sizeof(unsigned int), st);   // the arrival counter; the error word next to it is sticky
   void* args[] = {(void*)&p};
-  cudaError_t e = cudaLaunchCooperativeKernel((const void*)depth_frame_kernel, dim3(pl->grid), dim3(DF_THREADS), args, pl->smem, st);
+  const void* fn = pl->stages == 6 ? (const void*)depth_frame_kernel<6> : (const void*)depth_frame_kernel<4>;
+  cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(pl->grid), dim3(DF_THREADS), args, pl->smem, st);
   count_launch();
   if (e != cudaSuccess) {
     set_error("depth_frame_run: cooperative launch failed: %s", cudaGetErrorString(e));
