@@ -16,6 +16,8 @@
 // bf16 roundings follow the eager reference: a linear's output is rounded before the residual / embedding add.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "../../include/rstnet_b200.h"
 
@@ -64,6 +66,7 @@ struct DepthFrameParams {
   const bf16* w_gout[DF_MAXL][DF_MAXQ];  // gating linear_out, K padded    [D][Hp]
   const bf16* w_head[DF_MAXQ];        // audio_linears[k]              [card][D]
   int top_k; float temp; unsigned int seed; const long long* frame_counter; int n_valid[DF_MAXQ];
+  int dbg;               // profiling aid (RSTNET_DEPTH_DBG): bit 0 skip the MMA loop, bit 1 skip the cp.async loads, bit 2 skip the epilogue
   long long* trace;      // profiling aid (RSTNET_DEPTH_TRACE): CTA 0 stamps clock64 after every phase and every barrier
 };
 
@@ -214,6 +217,7 @@ __device__ void gemm_phase(const DepthFrameParams& p, uint8_t* smem, const bf16*
       if (units[i] < nunits) U = i + 1;
     }
     auto issue = [&](int c, bool with_w) {
+      if (p.dbg & 2) { cp_async_commit(); return; }
       const int s = c % STAGES;
       const uint32_t xs = smem_base + s * stage_bytes, ws = xs + x_bytes;
       const int k0 = c * DF_KC;
@@ -251,6 +255,7 @@ __device__ void gemm_phase(const DepthFrameParams& p, uint8_t* smem, const bf16*
       const int s = c % STAGES;
       const uint32_t xs = smem_base + s * stage_bytes, ws = xs + x_bytes;
       const int k0 = c * DF_KC;
+      if (p.dbg & 1) continue;
 #pragma unroll
       for (int ks = 0; ks < DF_KC / 16; ++ks) {
         uint32_t bfrag[2][2];
@@ -286,7 +291,7 @@ __device__ void gemm_phase(const DepthFrameParams& p, uint8_t* smem, const bf16*
     const int g = lane >> 2, t = lane & 3;
 #pragma unroll
     for (int i = 0; i < DF_MAXU; ++i) {
-      if (i >= U) continue;
+      if (i >= U || (p.dbg & 4)) continue;
       const int u = units[i];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
@@ -486,7 +491,7 @@ extern "C" int rstnet_lm_depth_frame_create(const rstnet_depth_frame_desc* d, rs
       RSTNET_REQUIRE(p.w_gin[l][k] && p.w_gout[l][k], "depth_frame_create: null gating weight (layer %d step %d)", l, k);
     }
   }
-  p.top_k = 0; p.temp = 1.f; p.seed = 0; p.frame_counter = nullptr; p.trace = nullptr;
+  p.top_k = 0; p.temp = 1.f; p.seed = 0; p.frame_counter = nullptr; p.trace = nullptr; p.dbg = 0;
   for (int k = 0; k < DF_MAXQ; ++k) p.n_valid[k] = d->card;
   const int Mpad = (d->M + 7) & ~7;
   pl->stages = d->M <= 64 ? 6 : 4;
@@ -519,6 +524,7 @@ extern "C" int rstnet_lm_depth_frame_run(const rstnet_depth_plan* pl, int32_t k_
   p.top_k = top_k; p.temp = temp; p.seed = seed; p.frame_counter = (const long long*)frame_counter;
   p.emb0_rows = (const bf16*)step0_embedding;
   p.trace = pl->trace;
+  { const char* e = getenv("RSTNET_DEPTH_DBG"); p.dbg = e ? atoi(e) : 0; }
   for (int k = 0; k < pl->p.Q; ++k) {
     int nv = n_valid ? n_valid[k] : p.card;
     if (nv <= 0 || nv > p.card) nv = p.card;

@@ -232,8 +232,11 @@ class GPT(nn.Module):
         self._local_states: Dict[int, "_LMState"] = {}
         self._ns_state: Optional["_LMState"] = None      # scratch scope of the non-streaming forward_global
         self.use_cuda_graphs = True
-        # the depth transformer of a frame as one persistent kernel (False: one launch per GEMM / attention / sampler)
-        self.use_depth_frame_kernel = True
+        # True: the depth transformer of a frame as ONE persistent cooperative kernel (csrc/lm_depth_frame.cu) instead of one
+        # launch per GEMM / attention / sampler.  Parity-tested, but measured SLOWER on B200 at the 7B shapes (5.3 ms vs
+        # 3.7 ms per frame at B = 64: the per-CTA activation-panel reads from L2 and the mma.sync dependency chains do not
+        # overlap, and 264 grid barriers cost 0.55 ms by themselves -- DESIGN.md §6), so it is opt-in.
+        self.use_depth_frame_kernel = False
 
     # ---- state_dict keys identical to the reference (`codecformer.` / `codecformer_text_emb.` subtrees are
     # stored under private attribute names because `codecformer` / `codecformer_text_emb` are API objects here)

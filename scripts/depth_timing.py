@@ -37,6 +37,11 @@ def one(B):
         r["depth_8steps_sampled_ms"] = timeit(lambda: st._depth_frame(0, 8, True, True, 30, 0.8, [2048] * 8))
         r["depth_8steps_nosample_ms"] = timeit(lambda: st._depth_frame(0, 8, True, False))
         r["depth_1step_nosample_ms"] = timeit(lambda: st._depth_frame(0, 1, True, False))
+        import os
+        for dbg, nm in ((1, "no_mma"), (2, "no_loads"), (4, "no_epilogue"), (7, "barriers_only")):
+            os.environ["RSTNET_DEPTH_DBG"] = str(dbg)
+            r[f"depth_1step_{nm}_ms"] = timeit(lambda: st._depth_frame(0, 1, True, False))
+        os.environ["RSTNET_DEPTH_DBG"] = "0"
         # per-phase stamps of CTA 0 for one step (k = 3)
         from rstnet_b200 import _lib
         tr = torch.zeros(1024, dtype=torch.int64, device=dev)

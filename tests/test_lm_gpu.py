@@ -663,7 +663,7 @@ def test_depth_frame_kernel_vs_multi_launch_path(small_lm):
         new, new_t, new_s = run(True)
         old, old_t, old_s = run(False)
     finally:
-        m.use_depth_frame_kernel = True
+        m.use_depth_frame_kernel = False
         m._packed = None
     for a, b in zip(new, old):
         assert _cos(a, b) >= 0.9995 and _rel(a, b) <= 3e-2, (_cos(a, b), _rel(a, b))
