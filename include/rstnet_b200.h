@@ -265,6 +265,14 @@ int rstnet_lm_rope_kv_append_bf16(const void* qkv, const void* cos_tab, const vo
                                   const int64_t* offset, int32_t offset_stride /* 0 shared, 1 per stream */, void* q_out,
                                   void* kv, int32_t rows, int32_t B, int32_t n_head, int32_t n_kv, int32_t hs, int32_t cap,
                                   rstnet_stream_t stream);
+/* ---- Kyutai pair-RoPE for the Moshi-style LMModel's temporal transformer (models/model.py:364-389; modules/rope.py:11-68,
+ * modules/transformer.py:391-399): qkv [rows][3][H][hd] ((p h d) layout); (even, odd) pairs of q / k rotate by
+ * freqs[p] * (offset + tl) (freqs [hd/2] fp32 = exp(-ln(max_period) * 2 p / hd), from the host), fp32 inside, one rounding
+ * to bf16; rotated q -> q_out [rows][H*hd],
+ * rotated k and v -> kv[2][B][H][cap][hd] at slot pos % cap.  Rows / offsets as rstnet_lm_rope_kv_append_bf16. */
+int rstnet_lm_rope_pair_kv_append_bf16(const void* qkv, const int64_t* offset, int32_t offset_stride, void* q_out, void* kv,
+                                       int32_t rows, int32_t B, int32_t H, int32_t hd, int32_t cap, const float* freqs,
+                                       rstnet_stream_t stream);
 /* ---- one query position per row over the ring with RingKVCache.complete's position labels and the
  * (pos_k>=0)&(delta>=0)&(delta<context) mask (llama_streaming.py:983-992), fp32 softmax. HBM-bound.  Rows as above;
  * every position of the launch must already be in the ring and no slot a query needs may have been overwritten

@@ -23,6 +23,7 @@ SYMBOLS = [
     "rstnet_rvq_decode_gather_f32",
     "rstnet_skinny_gemm_workspace", "rstnet_skinny_gemm_create", "rstnet_skinny_gemm_create_fused", "rstnet_skinny_gemm_run", "rstnet_skinny_gemm_destroy",
     "rstnet_lm_embed_sum_bf16", "rstnet_lm_embed_rows_bf16", "rstnet_lm_rms_norm_bf16", "rstnet_lm_rope_kv_append_bf16",
+    "rstnet_lm_rope_pair_kv_append_bf16",
     "rstnet_lm_ring_decode_attention_bf16", "rstnet_lm_silu_mul_bf16", "rstnet_lm_depth_attention_bf16", "rstnet_lm_sample_bf16",
     "rstnet_lm_depth_frame_create", "rstnet_lm_depth_frame_run", "rstnet_lm_depth_frame_destroy", "rstnet_lm_depth_frame_set_trace",
 ]
@@ -130,6 +131,7 @@ def lib() -> C.CDLL:
     L.rstnet_device_error_flags.restype = C.c_uint32
     L.rstnet_lm_rms_norm_bf16.argtypes = [vp, vp, vp, i32, i32, f32, i32, vp]
     L.rstnet_lm_rope_kv_append_bf16.argtypes = [vp, vp, vp, i64, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    L.rstnet_lm_rope_pair_kv_append_bf16.argtypes = [vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, vp, vp]
     L.rstnet_lm_ring_decode_attention_bf16.argtypes = [vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp]
     L.rstnet_lm_silu_mul_bf16.argtypes = [vp, vp, i32, i32, vp]
     L.rstnet_lm_depth_attention_bf16.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, vp]

@@ -136,6 +136,41 @@ __global__ void rope_kv_append_bf16_kernel(const bf16* __restrict__ qkv, const b
   for (int d = threadIdx.x; d < hs; d += blockDim.x) vdst[d] = vsrc[d];
 }
 
+// ---------------------------------------------------------------- Kyutai pair-RoPE (bf16 model) + KV ring append
+// The Moshi-style LMModel's temporal transformer (models/model.py:364-389 over modules/transformer.py:375-419):
+// qkv [row][3][H][hd] ((p h d) layout, transformer.py:391-393); (even, odd) pairs of q and k rotate by
+// freqs[d/2] * (offset + tl) with everything in fp32 and ONE rounding to bf16 at the end (modules/rope.py:36-66);
+// rotated q -> q_out [row][H*hd], rotated k and v -> kv[2][B][H][cap][hd] at slot pos % cap.
+__global__ void rope_pair_kv_append_bf16_kernel(const bf16* __restrict__ qkv, const long long* __restrict__ offset, int ostride,
+                                                bf16* __restrict__ q_out, bf16* __restrict__ kv, int B, int H, int hd, int cap,
+                                                const float* __restrict__ freqs) {
+  const int row = blockIdx.x / H, h = blockIdx.x % H;
+  const int b = row % B;
+  const long long off = offset[(long long)b * ostride];
+  const long long pos = off + row / B;
+  const int slot = (int)(pos % cap);
+  const int HD = H * hd;
+  const bf16* q = qkv + (long long)row * 3 * HD + h * hd;
+  const bf16* k = q + HD;
+  const bf16* v = q + 2 * HD;
+  bf16* kdst = kv + (((long long)b * H + h) * cap + slot) * hd;
+  bf16* vdst = kv + (long long)B * H * cap * hd + (((long long)b * H + h) * cap + slot) * hd;
+  const float ts = __fadd_rn((float)off, (float)(row / B));     // offset.float() + arange(T) in fp32 (rope.py:37)
+  for (int pr = threadIdx.x; pr < hd / 2; pr += blockDim.x) {
+    const float ang = __fmul_rn(freqs[pr], ts);     // freqs = exp(ds * (-ln(max_period) * 2 / hd)) from the host (rope.py:35-36)
+    const float c = cosf(ang), s = sinf(ang);
+    const float qr = b2f(q[2 * pr]), qi = b2f(q[2 * pr + 1]);
+    const float kr = b2f(k[2 * pr]), ki = b2f(k[2 * pr + 1]);
+    bf16* qo = q_out + (long long)row * HD + h * hd;
+    qo[2 * pr] = f2b(__fsub_rn(__fmul_rn(qr, c), __fmul_rn(qi, s)));
+    qo[2 * pr + 1] = f2b(__fadd_rn(__fmul_rn(qr, s), __fmul_rn(qi, c)));
+    kdst[2 * pr] = f2b(__fsub_rn(__fmul_rn(kr, c), __fmul_rn(ki, s)));
+    kdst[2 * pr + 1] = f2b(__fadd_rn(__fmul_rn(kr, s), __fmul_rn(ki, c)));
+    vdst[2 * pr] = v[2 * pr];
+    vdst[2 * pr + 1] = v[2 * pr + 1];
+  }
+}
+
 // ---------------------------------------------------------------- ring decode attention (one query position per row)
 // one CTA per (G query heads sharing a kv head, row); 8 lanes share a key row (16 dims = 32 bytes each, so a warp load
 // covers 4 whole 256-byte rows = 1 KB contiguous); per-group online softmax, combined across groups / warps at the end.
@@ -372,6 +407,18 @@ extern "C" int rstnet_lm_rope_kv_append_bf16(const void* qkv, const void* cos_ta
                                                                            rope_n, rope_rows);
   count_launch();
   return check_launch("lm_rope_kv_append");
+}
+
+extern "C" int rstnet_lm_rope_pair_kv_append_bf16(const void* qkv, const int64_t* offset, int32_t offset_stride, void* q_out, void* kv,
+                                                  int32_t rows, int32_t B, int32_t H, int32_t hd, int32_t cap, const float* freqs,
+                                                  rstnet_stream_t stream) {
+  RSTNET_REQUIRE(qkv && offset && q_out && kv && freqs, "lm_rope_pair_kv_append: null pointer");
+  RSTNET_REQUIRE(rows > 0 && B > 0 && rows % B == 0 && H > 0 && hd > 0 && hd % 2 == 0 && cap > 0, "lm_rope_pair_kv_append: bad shape");
+  rope_pair_kv_append_bf16_kernel<<<rows * H, 64, 0, (cudaStream_t)stream>>>((const bf16*)qkv, (const long long*)offset,
+                                                                             offset_stride ? 1 : 0, (bf16*)q_out, (bf16*)kv, B, H, hd,
+                                                                             cap, freqs);
+  count_launch();
+  return check_launch("lm_rope_pair_kv_append");
 }
 
 extern "C" int rstnet_lm_ring_decode_attention_bf16(const void* q, const void* kv, const int64_t* offset, int32_t offset_stride,

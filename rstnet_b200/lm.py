@@ -238,6 +238,11 @@ class GPT(nn.Module):
         # overlap, and 264 grid barriers cost 0.55 ms by themselves -- DESIGN.md §6), so it is opt-in.
         self.use_depth_frame_kernel = False
 
+    # parameter names of the depth transformer (the Moshi-style LMModel of rstnet_b200/moshi.py has the same structure under
+    # other names, models/model.py:188-224)
+    _DN = dict(din="codecformer_in.{}.weight", demb="codecformer_emb.{}.weight", dtext="codecformer_text_emb_.weight",
+               dlayer="codecformer_.layers.{}", dhead="audio_linears.{}.weight")
+
     # ---- state_dict keys identical to the reference (`codecformer.` / `codecformer_text_emb.` subtrees are
     # stored under private attribute names because `codecformer` / `codecformer_text_emb` are API objects here)
     _RENAME = (("codecformer_.", "codecformer."), ("codecformer_text_emb_.", "codecformer_text_emb."))
@@ -528,14 +533,12 @@ class _LMState:
             return torch.zeros(*shape, dtype=dtype, device=dev)
 
         if m._packed is None:
-            pk = {f"fc12.{l}": torch.cat([P[f"transformer.h.{l}.mlp.fc_1.linear.weight"],
-                                          P[f"transformer.h.{l}.mlp.fc_2.linear.weight"]], 0).contiguous()
-                  for l in range(c.n_layer)}
+            pk = self._pack_temporal(P)
             if Hp != H or self.frame_kernel:
                 for l in range(c.codecformer_layers):
                     for k in range(c.dep_q):
-                        w_in = P[f"codecformer_.layers.{l}.gating.{k}.linear_in.weight"]
-                        w_out = P[f"codecformer_.layers.{l}.gating.{k}.linear_out.weight"]
+                        w_in = P[m._DN["dlayer"].format(l) + f".gating.{k}.linear_in.weight"]
+                        w_out = P[m._DN["dlayer"].format(l) + f".gating.{k}.linear_out.weight"]
                         gi = z(2 * Hp, D)
                         gi[:H], gi[Hp:Hp + H] = w_in[:H], w_in[H:]
                         if self.frame_kernel:
@@ -560,56 +563,7 @@ class _LMState:
         self.has_temporal = "temporal" in parts
 
         if self.has_temporal:
-            self.seq = z(M, c.n_q + 1, dtype=torch.int64)
-            self.x, self.xn, self.q, self.att = z(M, E), z(M, E), z(M, nh * hs), z(M, nh * hs)
-            self.qkv, self.hmid = z(M, (nh + 2 * nkv) * hs), z(M, I)
-            self.out, self.logits = z(M, E), z(M, V)
-            if parent is None:
-                # one position counter per stream (per-stream reset / admission), mirrored on the host for the
-                # block_size check (under graph replay the device cannot raise)
-                self.offset = z(B, dtype=torch.int64)
-                self.pos_host = np.zeros(B, dtype=np.int64)
-                # advance flags: a stream with 0 is HELD by the next steps (frame scheduler rows without input)
-                self.active = torch.ones(B, dtype=torch.int64, device=dev)
-                self.active_host = np.ones(B, dtype=np.int64)
-                # KV rings, one K/V row per KV GROUP: [2, B, n_kv, cap, hs] (lit_model.py:607-615 stores n_head copies)
-                self.kv = [z(2, B, nkv, self.cap, hs) for _ in range(c.n_layer)]
-                # RoPE tables in the model dtype (the reference's buffers are cast by .to(bfloat16)); lit_model.py:441-488
-                n = c.rope_n_elem
-                theta = 1.0 / (c.rope_base ** (torch.arange(0, n, 2).float() / n))
-                if c.rope_adjustments is not None:
-                    ec = c.rope_adjustments
-                    wavelen = 2 * torch.pi / theta
-                    ratio = ec["original_max_seq_len"] / wavelen
-                    smooth = torch.clamp((ratio - ec["low_freq_factor"]) / (ec["high_freq_factor"] - ec["low_freq_factor"]), min=0.0, max=1.0)
-                    theta = (1 - smooth) * (theta / ec["factor"]) + smooth * theta
-                idx_theta = torch.outer(torch.arange(c.block_size) / c.rope_condense_ratio, theta).repeat(1, 2)
-                self.cos, self.sin = torch.cos(idx_theta).to(bf).to(dev).contiguous(), torch.sin(idx_theta).to(bf).to(dev).contiguous()
-            else:
-                self.offset, self.pos_host, self.kv, self.cos, self.sin = parent.offset, parent.pos_host, parent.kv, parent.cos, parent.sin
-                self.active, self.active_host = parent.active, parent.active_host
-            self.tables = [P[f"input_emb.{i}.weight"] for i in range(c.n_q)]
-            self.table_ptrs = torch.tensor([t.data_ptr() for t in self.tables], dtype=torch.int64, device=dev)
-            self.wte = P["transformer.wte.weight"]
-            L_ = c.n_layer
-            n1 = [P[f"transformer.h.{l}.norm_1.weight"] for l in range(L_)]
-            n2 = [P[f"transformer.h.{l}.norm_2.weight"] for l in range(L_)]
-            self.ln_f = P["transformer.ln_f.weight"]
-            self.n1_first = n1[0]
-            self.layers = []
-            for l in range(L_):
-                p = f"transformer.h.{l}"
-                last = l == L_ - 1
-                self.layers.append(dict(
-                    qkv=G(self.xn, P[f"{p}.attn.attn.linear.weight"], self.qkv),
-                    # x = attn + x ; xn = norm_2(x)   (Block.forward, llama_streaming.py:846-849) in the GEMM's finalize
-                    proj=G(self.att, P[f"{p}.attn.proj.linear.weight"], self.x, self.x, norm_w=n2[l], aux=self.xn, eps=c.norm_eps),
-                    # hmid = silu(fc_1 x) * fc_2 x   (LLaMAMLP, lit_model.py:399-403)
-                    fc=G(self.xn, m._packed[f"fc12.{l}"], None, silu_out=self.hmid),
-                    # x = mlp + x ; xn = norm_1 of the next block (or ln_f -> transformer_out)
-                    down=G(self.hmid, P[f"{p}.mlp.proj.linear.weight"], self.x, self.x, norm_w=self.ln_f if last else n1[l + 1],
-                           aux=self.out if last else self.xn, eps=c.norm_eps)))
-            self.head = G(self.out, P["lm_head.linear.weight"], self.logits)
+            self._build_temporal(P, G, z, parent)
 
         if "depth" in parts:
             self.tout = z(M, E)
@@ -623,16 +577,17 @@ class _LMState:
             self.dkv = [self.dkv_all[l] for l in range(c.codecformer_layers)]
             self.df = None
             # depth transformer: per-codebook-step weight slabs
-            self.text_emb = P["codecformer_text_emb_.weight"]
-            self.dep_emb = [P[f"codecformer_emb.{i}.weight"] for i in range(c.dep_q - 1)]
+            DN = m._DN
+            self.text_emb = P[DN["dtext"]]
+            self.dep_emb = [P[DN["demb"].format(i)] for i in range(c.dep_q - 1)]
             Ld = c.codecformer_layers
-            a1 = [P[f"codecformer_.layers.{l}.norm1.alpha"].view(-1) for l in range(Ld)]
-            a2 = [P[f"codecformer_.layers.{l}.norm2.alpha"].view(-1) for l in range(Ld)]
+            a1 = [P[DN["dlayer"].format(l) + ".norm1.alpha"].view(-1) for l in range(Ld)]
+            a2 = [P[DN["dlayer"].format(l) + ".norm2.alpha"].view(-1) for l in range(Ld)]
             self.dsteps = []
             for k in range(c.dep_q if not self.frame_kernel else 0):
                 layers = []
                 for l in range(Ld):
-                    p = f"codecformer_.layers.{l}"
+                    p = DN["dlayer"].format(l)
                     w_in = P[f"{p}.self_attn.in_proj_weight"].view(c.dep_q, 3 * D, D)[k]
                     w_out = P[f"{p}.self_attn.out_proj.weight"].view(c.dep_q, D, D)[k]
                     g_in = m._packed.get(f"gin.{l}.{k}", P[f"{p}.gating.{k}.linear_in.weight"])
@@ -644,10 +599,73 @@ class _LMState:
                         gin=G(self.dn, g_in, None, silu_out=self.dh),
                         gout=G(self.dh, g_out, self.dx, self.dx, **nxt)))
                 self.dsteps.append(dict(
-                    inp=G(self.tout, P[f"codecformer_in.{k}.weight"], self.dx, self.demb, norm_w=a1[0], aux=self.dn, eps=1e-8, kyutai=True),
-                    layers=layers, head=G(self.dx, P[f"audio_linears.{k}.weight"], self.dlogits)))
+                    inp=G(self.tout, P[DN["din"].format(k)], self.dx, self.demb, norm_w=a1[0], aux=self.dn, eps=1e-8, kyutai=True),
+                    layers=layers, head=G(self.dx, P[DN["dhead"].format(k)], self.dlogits)))
             if self.frame_kernel:
                 self._build_depth_frame(P)
+
+    def _pack_temporal(self, P):
+        """one-time repacked weights of the temporal transformer (fc_1 | fc_2 as one GEMM)"""
+        c = self.c
+        return {f"fc12.{l}": torch.cat([P[f"transformer.h.{l}.mlp.fc_1.linear.weight"],
+                                        P[f"transformer.h.{l}.mlp.fc_2.linear.weight"]], 0).contiguous()
+                for l in range(c.n_layer)}
+
+    def _build_temporal(self, P, G, z, parent):
+        m, c, B, M = self.m, self.c, self.B, self.M
+        dev, bf = m.device, torch.bfloat16
+        E, V, I = c.n_embd, c.padded_vocab_size, c.intermediate_size
+        nh, nkv, hs = c.n_head, c.n_query_groups, c.head_size
+        self.seq = z(M, c.n_q + 1, dtype=torch.int64)
+        self.x, self.xn, self.q, self.att = z(M, E), z(M, E), z(M, nh * hs), z(M, nh * hs)
+        self.qkv, self.hmid = z(M, (nh + 2 * nkv) * hs), z(M, I)
+        self.out, self.logits = z(M, E), z(M, V)
+        if parent is None:
+            # one position counter per stream (per-stream reset / admission), mirrored on the host for the
+            # block_size check (under graph replay the device cannot raise)
+            self.offset = z(B, dtype=torch.int64)
+            self.pos_host = np.zeros(B, dtype=np.int64)
+            # advance flags: a stream with 0 is HELD by the next steps (frame scheduler rows without input)
+            self.active = torch.ones(B, dtype=torch.int64, device=dev)
+            self.active_host = np.ones(B, dtype=np.int64)
+            # KV rings, one K/V row per KV GROUP: [2, B, n_kv, cap, hs] (lit_model.py:607-615 stores n_head copies)
+            self.kv = [z(2, B, nkv, self.cap, hs) for _ in range(c.n_layer)]
+            # RoPE tables in the model dtype (the reference's buffers are cast by .to(bfloat16)); lit_model.py:441-488
+            n = c.rope_n_elem
+            theta = 1.0 / (c.rope_base ** (torch.arange(0, n, 2).float() / n))
+            if c.rope_adjustments is not None:
+                ec = c.rope_adjustments
+                wavelen = 2 * torch.pi / theta
+                ratio = ec["original_max_seq_len"] / wavelen
+                smooth = torch.clamp((ratio - ec["low_freq_factor"]) / (ec["high_freq_factor"] - ec["low_freq_factor"]), min=0.0, max=1.0)
+                theta = (1 - smooth) * (theta / ec["factor"]) + smooth * theta
+            idx_theta = torch.outer(torch.arange(c.block_size) / c.rope_condense_ratio, theta).repeat(1, 2)
+            self.cos, self.sin = torch.cos(idx_theta).to(bf).to(dev).contiguous(), torch.sin(idx_theta).to(bf).to(dev).contiguous()
+        else:
+            self.offset, self.pos_host, self.kv, self.cos, self.sin = parent.offset, parent.pos_host, parent.kv, parent.cos, parent.sin
+            self.active, self.active_host = parent.active, parent.active_host
+        self.tables = [P[f"input_emb.{i}.weight"] for i in range(c.n_q)]
+        self.table_ptrs = torch.tensor([t.data_ptr() for t in self.tables], dtype=torch.int64, device=dev)
+        self.wte = P["transformer.wte.weight"]
+        L_ = c.n_layer
+        n1 = [P[f"transformer.h.{l}.norm_1.weight"] for l in range(L_)]
+        n2 = [P[f"transformer.h.{l}.norm_2.weight"] for l in range(L_)]
+        self.ln_f = P["transformer.ln_f.weight"]
+        self.n1_first = n1[0]
+        self.layers = []
+        for l in range(L_):
+            p = f"transformer.h.{l}"
+            last = l == L_ - 1
+            self.layers.append(dict(
+                qkv=G(self.xn, P[f"{p}.attn.attn.linear.weight"], self.qkv),
+                # x = attn + x ; xn = norm_2(x)   (Block.forward, llama_streaming.py:846-849) in the GEMM's finalize
+                proj=G(self.att, P[f"{p}.attn.proj.linear.weight"], self.x, self.x, norm_w=n2[l], aux=self.xn, eps=c.norm_eps),
+                # hmid = silu(fc_1 x) * fc_2 x   (LLaMAMLP, lit_model.py:399-403)
+                fc=G(self.xn, m._packed[f"fc12.{l}"], None, silu_out=self.hmid),
+                # x = mlp + x ; xn = norm_1 of the next block (or ln_f -> transformer_out)
+                down=G(self.hmid, P[f"{p}.mlp.proj.linear.weight"], self.x, self.x, norm_w=self.ln_f if last else n1[l + 1],
+                       aux=self.out if last else self.xn, eps=c.norm_eps)))
+        self.head = G(self.out, P["lm_head.linear.weight"], self.logits)
 
     def _build_depth_frame(self, P):
         c, M = self.c, self.M
@@ -665,12 +683,12 @@ class _LMState:
         d.tokens, d.barrier = self.tokens.data_ptr(), self.df_sync.data_ptr()
         pk = self.m._packed
         for k in range(c.dep_q):
-            d.w_in[k] = P[f"codecformer_in.{k}.weight"].data_ptr()
+            d.w_in[k] = P[self.m._DN["din"].format(k)].data_ptr()
             tab = self.text_emb if k == 0 else self.dep_emb[k - 1]
             d.emb[k], d.emb_rows[k] = tab.data_ptr(), tab.shape[0]
-            d.w_head[k] = P[f"audio_linears.{k}.weight"].data_ptr()
+            d.w_head[k] = P[self.m._DN["dhead"].format(k)].data_ptr()
         for l in range(c.codecformer_layers):
-            p = f"codecformer_.layers.{l}"
+            p = self.m._DN["dlayer"].format(l)
             d.w_qkv[l] = P[f"{p}.self_attn.in_proj_weight"].data_ptr()
             d.w_out[l] = P[f"{p}.self_attn.out_proj.weight"].data_ptr()
             d.a1[l], d.a2[l] = P[f"{p}.norm1.alpha"].data_ptr(), P[f"{p}.norm2.alpha"].data_ptr()

@@ -169,3 +169,33 @@ def test_frame_scheduler_host_logic():
     with pytest.raises(RuntimeError):
         s.admit("E")                                    # full
     assert s.free_rows() == 0 and s.sessions() == {"B": 1, "C": 0, "D": 2}
+
+
+def test_moshi_oracle_reproduces_reference_lmgen(golden_dir):
+    """oracle/moshi_oracle.py (LMModel.forward_text / depformer_step / LMGen.step, models/model.py:364-597) against the
+    unmodified reference's fp32 tokens (tests/golden/moshi_small.npz)."""
+    from oracle import moshi_oracle as M
+    gold = np.load(os.path.join(golden_dir, "moshi_small.npz"))
+    cfg = M.SMALL
+    w = M.synthetic_weights(cfg, seed=5)
+    inputs = torch.from_numpy(gold["inputs"])
+    ref = torch.from_numpy(gold["f32_out"])
+    ora = M.LMGenOracle(w, cfg, inputs.shape[1])
+    outs = []
+    with torch.no_grad():
+        for t in range(8):
+            o = ora.step(inputs[t])
+            assert (o is None) == (t < max(cfg.delays))
+            if o is not None:
+                outs.append(o)
+    mine = torch.stack(outs)
+    agree = float((mine == ref[:len(outs)]).float().mean())
+    assert agree >= 0.9, agree        # bit-equal on the generating machine; a BLAS with another summation order may flip near-ties
+    # product class: same state_dict keys as the reference module
+    from rstnet_b200.moshi import LMModel
+    m = LMModel(**cfg.reference_kwargs())
+    assert set(m.state_dict().keys()) == set(w.keys())
+    m.load_state_dict(w, strict=True)
+    assert m.num_codebooks == 17 and m.initial_token_id == cfg.card and m.text_initial_token_id == cfg.text_card
+    with pytest.raises(NotImplementedError):
+        LMModel(**{**cfg.reference_kwargs(), "norm": "layer_norm"})
