@@ -98,6 +98,7 @@ def test_lmgen_step_closed_loop(moshi):
     gen2 = LMGen(m, use_sampling=False)
     ora = M.LMGenOracle({k: v.to(BF) for k, v in w.items()}, cfg, B)
     exact = n = 0
+    worst = 0.0
     with gen2.streaming(B), torch.no_grad():
         for t in range(inputs.shape[0]):
             gen2.step(inputs[t].to(DEV))
