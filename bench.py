@@ -26,6 +26,7 @@ Next to the headline (N = 1 only, extra keys, each its own unit of work and outs
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -277,6 +278,7 @@ def run_ours(args):
                     extras[name] = fn()
                 except Exception as e:
                     extras[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                gc.collect()              # streaming states hold reference cycles (plans <-> closures): free their HBM now
                 torch.cuda.empty_cache()
             guarded("gpu_eager_codec", lambda: gpu_eager_codec_baseline(dev, B))
             m._stream_state = None
@@ -658,6 +660,7 @@ def cfg5_duplex_bench(dev, S, ticks: int = 40):
         lm._state = None
         codec._stream_state = None
         eng = sch = None
+        gc.collect()
         torch.cuda.empty_cache()
     ok = [r["streams"] for r in res["runs"] if r.get("realtime")]
     res["realtime_streams_per_gpu"] = max(ok) if ok else 0

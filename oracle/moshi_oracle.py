@@ -166,13 +166,15 @@ class MoshiStream:
         out = L.rms_norm_f32(x, w["out_norm.alpha"])
         return out, F.linear(out, w["text_linear.weight"])[:, None]
 
-    def depformer_step(self, text_token: torch.Tensor, transformer_out: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        """LMGen.depformer_step, greedy (:564-597): tokens [B, dep_q], logits [B, dep_q, card]."""
+    def depformer_step(self, text_token: torch.Tensor, transformer_out: torch.Tensor,
+                       force: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        """LMGen.depformer_step, greedy (:564-597): tokens [B, dep_q], logits [B, dep_q, card].
+        force [B, dep_q]: teacher-force these audio tokens (the logits are then those a candidate's decisions are judged on)."""
         self.depth.start_depth()
         prev, toks, lgs = text_token, [], []
         for k in range(self.cfg.dep_q):
             lg = self.depth.forward_codecformer(k, prev[:, None, None], transformer_out)
-            nxt = torch.argmax(lg.float(), dim=-1)[:, 0, 0]
+            nxt = torch.argmax(lg.float(), dim=-1)[:, 0, 0] if force is None else force[:, k]
             toks.append(nxt); lgs.append(lg[:, 0, 0])
             prev = nxt
         return torch.stack(toks, 1), torch.stack(lgs, 1)
@@ -192,7 +194,8 @@ class LMGenOracle:
         self.offset = 0
         self.last = None
 
-    def step(self, input_tokens: torch.Tensor) -> Optional[torch.Tensor]:
+    def step(self, input_tokens: torch.Tensor, force: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+        """force [B, dep_q + 1]: the (text, audio) tokens to take at this step instead of the oracle's own argmaxes."""
         cfg = self.cfg
         CT = self.cache.shape[2]
         for q_other in range(input_tokens.shape[1]):
@@ -205,8 +208,8 @@ class LMGenOracle:
                 self.cache[:, k, position] = self.initial[:, k, 0]
         input_ = self.cache[:, :, position:position + 1]
         out, text_logits = self.lm.forward_text(input_)
-        text_token = torch.argmax(text_logits.float(), dim=-1)[:, 0, 0]
-        audio, alog = self.lm.depformer_step(text_token, out)
+        text_token = torch.argmax(text_logits.float(), dim=-1)[:, 0, 0] if force is None else force[:, 0]
+        audio, alog = self.lm.depformer_step(text_token, out, None if force is None else force[:, 1:])
         self.last = (input_.clone(), out, text_logits, alog)
         self.offset += 1
         position = self.offset % CT

@@ -176,6 +176,9 @@ class MimiCodec(nn.Module):
         self.decoder_precision = 0
         # resblock convs (k=3 C->C/2, 1x1 C/2->C) on the tensor cores too; False keeps them on the CUDA-core kernel
         self.resblock_tensor_cores = True
+        # non-streaming encode / decode of a batch (offline tokenization): batches of at least this many
+        # clips run the tcgen05 path (a 128-row tile = 128 clips at one time step), smaller ones the fp32 CUDA-core path
+        self.batch_tensor_cores_min = 96
 
     # ------------------------------------------------------------------ parameters
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
@@ -478,19 +481,21 @@ class _Engine:
 
     # ------------------------------------------------------------------ plans
     def enc_plan(self, B: int, L: int) -> "_EncPlan":
-        key = ("enc", B, L)
+        tc = B >= self.m.batch_tensor_cores_min
+        key = ("enc", B, L, tc)
         if key not in self._plans:
             for k in [k for k in self._plans if k[0] == "enc"]:  # keep one batch-mode plan per kind alive
                 del self._plans[k]
-            self._plans[key] = _EncPlan(self, B, L, streaming=False, tensor_cores=False)
+            self._plans[key] = _EncPlan(self, B, L, streaming=False, tensor_cores=tc)
         return self._plans[key]
 
     def dec_plan(self, B: int, T: int) -> "_DecPlan":
-        key = ("dec", B, T)
+        tc = B >= self.m.batch_tensor_cores_min
+        key = ("dec", B, T, tc)
         if key not in self._plans:
             for k in [k for k in self._plans if k[0] == "dec"]:
                 del self._plans[k]
-            self._plans[key] = _DecPlan(self, B, T, streaming=False, tensor_cores=False)
+            self._plans[key] = _DecPlan(self, B, T, streaming=False, tensor_cores=tc)
         return self._plans[key]
 
     # ------------------------------------------------------------------ non-streaming entry points

@@ -18,7 +18,7 @@ if [ "$STAGE" = "all" ] || [ "$STAGE" = "ncu" ]; then
   python scripts/ncu_traffic.py gpurun_out/r2_codec_metrics.csv gpurun_out/r2_traffic.json "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none; python bench.py --frames 3 --steps 1 --warmup 3 --no-lm" | tee gpurun_out/r2_traffic.txt
 fi
 if [ "$STAGE" = "all" ] || [ "$STAGE" = "sanitizer" ]; then
-  timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gemm_tc_gpu.py -x -q 2>&1 | tail -25 > gpurun_out/r2_sanitizer_memcheck.log
+  timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gemm_tc_gpu.py -x -q 2>&1 | grep -v "Host Frame" | head -60 > gpurun_out/r2_sanitizer_memcheck.log
   timeout 600 compute-sanitizer --tool racecheck --print-limit 20 python -m pytest tests/test_gemm_tc_gpu.py -x -q -k "ts or persistent or conv" 2>&1 | tail -25 > gpurun_out/r2_sanitizer_racecheck.log
-  tail -4 gpurun_out/r2_sanitizer_memcheck.log gpurun_out/r2_sanitizer_racecheck.log
+  tail -n 4 gpurun_out/r2_sanitizer_memcheck.log; tail -n 4 gpurun_out/r2_sanitizer_racecheck.log
 fi

@@ -229,3 +229,42 @@ def test_frame_scheduler_with_duplex_engine(codec):
     assert len(eng.latencies_ms) == 9 and sch.free_rows() == 2
     lm.streaming_forever(1); lm._state = None
     codec._stream_state = None
+
+
+def test_offline_tokenization_and_batch_tensor_core_path(official_weights, codec, tmp_path):
+    """rstnet_b200.offline (offline_codec_tokenization.py / inference.py drivers): equal-length clips are batched, the dict
+    `utt -> int16 [8, T]` equals per-clip MimiTokenizer.tokenize and survives torch.save; a batch of >= 96 clips runs the
+    non-streaming tcgen05 path and must agree with the oracle wherever the margins allow; wav directory round trip."""
+    from rstnet_b200 import offline
+    tok = MimiTokenizer(codec, device=torch.device(DEV))
+    lens = [4000, 9600, 9600, 1920, 9600, 5000]
+    clips = {f"utt{i}": S.synthetic_audio(1, L, seed=300 + i)[0, 0] for i, L in enumerate(lens)}
+    toks = offline.tokenize_utterances(codec, clips.items(), batch_size=2)
+    assert set(toks) == set(clips)
+    for utt, wav in clips.items():
+        ref = tok.tokenize(wav[None], 24000)
+        assert toks[utt].dtype == torch.int16 and torch.equal(toks[utt], ref), utt
+    path = os.path.join(tmp_path, "codes.pt")
+    offline.save_tokens(toks, path)
+    back = torch.load(path)
+    assert all(torch.equal(back[k], toks[k]) for k in toks)
+    # a 128-clip batch: tensor-core batch plan vs the oracle
+    B, L = 128, 1920 * 3
+    x = S.synthetic_audio(B, L, seed=555)
+    with torch.no_grad():
+        ref_codes = O.encode(x, official_weights)
+        margins = O.rvq_margins(O.encode_latent(x, official_weights), official_weights).min(dim=0).values.view(B, -1)
+        ref_wav = O.decode(ref_codes, official_weights)
+    codes = codec.encode(x.to(DEV))
+    assert any(k[0] == "enc" and k[3] for k in codec._engine._plans), "the batch should have taken the tensor-core plan"
+    bad = (codes.cpu() != ref_codes).any(dim=1)
+    assert not bool((bad & (margins > MARGIN)).any())
+    wav = codec.decode(ref_codes.to(DEV))
+    assert _maxdiff(wav, ref_wav) <= 1e-4 * max(1.0, float(ref_wav.abs().max()))
+    # wav directory round trip (inference.py)
+    src, dst = os.path.join(tmp_path, "in"), os.path.join(tmp_path, "out")
+    os.makedirs(src)
+    offline.write_wav(os.path.join(src, "a.wav"), 0.5 * clips["utt1"] / clips["utt1"].abs().max())
+    assert offline.reconstruct_directory(codec, src, dst) == 1
+    rec, sr = offline.read_wav(os.path.join(dst, "a.wav"))
+    assert sr == 24000 and rec.numel() == 9600

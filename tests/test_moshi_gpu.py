@@ -93,8 +93,7 @@ def test_lmgen_step_closed_loop(moshi):
     same = (mine == ref).all(dim=(1, 2, 3))
     first_diff = int((~same).nonzero()[0]) if bool((~same).any()) else len(same)
     print(f"moshi LMGen closed loop: identical to the reference for the first {first_diff}/{len(same)} output frames")
-    assert first_diff >= 1
-    # decision-level check: run the product again, mirroring its generated tokens into the oracle step by step
+    # decision-level check: every (text, audio) decision of OUR closed loop under the oracle teacher-forced with our tokens
     gen2 = LMGen(m, use_sampling=False)
     ora = M.LMGenOracle({k: v.to(BF) for k, v in w.items()}, cfg, B)
     exact = n = 0
@@ -102,17 +101,18 @@ def test_lmgen_step_closed_loop(moshi):
     with gen2.streaming(B), torch.no_grad():
         for t in range(inputs.shape[0]):
             gen2.step(inputs[t].to(DEV))
-            ora.step(inputs[t])
-            CT = ora.cache.shape[2]
-            pos = ora.offset % CT
+            pos = gen2._st.offset % gen2._st.cache.shape[2]
             ours = gen2._st.cache[:, :cfg.dep_q + 1, pos].cpu()            # [B, 9] tokens we generated at this step
+            ora.step(inputs[t], force=ours)
             _, _, text_logits, alog = ora.last
-            lg_text = text_logits.float()[:, 0, 0]
-            d_text = lg_text.max(-1).values - lg_text.gather(1, ours[:, :1])[:, 0]
-            worst = max(worst, float(d_text.max()))
-            exact += int((d_text == 0).sum()); n += B
-            ora.cache[:, :cfg.dep_q + 1, pos] = ours                        # teacher-force the oracle with our decision
-    print(f"moshi LMGen: {exact}/{n} text decisions are the oracle's exact argmax; worst deficit {worst:.3f}")
+            lt = text_logits.float()[:, 0, 0]
+            d = [lt.max(-1).values - lt.gather(1, ours[:, :1])[:, 0]]
+            la = alog.float()                                               # [B, dep_q, card]
+            d.append((la.max(-1).values - la.gather(2, ours[:, 1:, None])[:, :, 0]).flatten())
+            d = torch.cat(d)
+            worst = max(worst, float(d.max()))
+            exact += int((d == 0).sum()); n += d.numel()
+    print(f"moshi LMGen: {exact}/{n} decisions are the oracle's exact argmax; worst deficit {worst:.3f}")
     assert worst <= 0.1 and exact >= 0.8 * n
     # reset restarts the generator
     with gen.streaming(B):
