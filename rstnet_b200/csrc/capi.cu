@@ -3,6 +3,7 @@
 #include "../../include/rstnet_b200.h"
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 
 namespace rstnet {
 
@@ -17,6 +18,15 @@ void set_error(const char* fmt, ...) {
 }
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RSTNET_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
 
 // Launch-configuration errors only (cudaGetLastError does not synchronise, and is legal during
 // stream capture); asynchronous faults surface at the caller's next synchronisation.

@@ -69,6 +69,9 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // everything above touched only this CTA's shared memory / TMEM: it overlaps the tail of the previous kernel (PDL)
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     for (int kit = 0; kit < k_count; ++kit) {
@@ -137,6 +140,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
 // plain finalize: out = bf16(sum_s partial[s] + R), 4 elements per thread (N % 4 == 0)
 __global__ void skinny_finalize_kernel(const float* __restrict__ partial, const __nv_bfloat16* __restrict__ R,
                                        __nv_bfloat16* __restrict__ out, long long MN, int splits) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long n4 = MN / 4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 v = *reinterpret_cast<const float4*>(partial + 4 * i);
@@ -170,6 +175,8 @@ skinny_finalize_norm_kernel(const float* __restrict__ partial, const __nv_bfloat
   cg::cluster_group cluster = cg::this_cluster();
   __shared__ float red[32];
   __shared__ float slice_ss;
+  pdl_launch_dependents();
+  pdl_wait();
   const int m = blockIdx.x / FIN_CL, slice = (int)cluster.block_rank();
   const int n_lo = slice * (N / FIN_CL), n_hi = n_lo + N / FIN_CL;
   const long long MN = (long long)M * N;
@@ -225,6 +232,8 @@ skinny_finalize_norm_kernel(const float* __restrict__ partial, const __nv_bfloat
 // finalize + SiLU gating: aux[m][c] = bf16(silu(bf16(a)) ) * bf16(b) with a = cols [0,I), b = cols [I,2I) of the GEMM result
 __global__ void skinny_finalize_silu_kernel(const float* __restrict__ partial, __nv_bfloat16* __restrict__ aux, int M, int N,
                                             int splits) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int I = N / 2;
   const long long MN = (long long)M * N, total = (long long)M * I;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -357,27 +366,27 @@ extern "C" int rstnet_skinny_gemm_run(const rstnet_skinny_plan* pl, rstnet_strea
   static unsigned long long attr = 0;
   smem_optin(gemm_skinny_kernel<4>, 200 * 1024, attr);
   cudaStream_t st = (cudaStream_t)stream;
-  gemm_skinny_kernel<4><<<pl->grid, SK_THREADS, pl->smem, st>>>(pl->tmW, pl->tmX, pl->p);
+  launch_pdl(gemm_skinny_kernel<4>, pl->grid, dim3(SK_THREADS), pl->smem, st, pl->tmW, pl->tmX, pl->p);
   count_launch();
   if (int e = check_launch("gemm_skinny")) return e;
   const long long MN = (long long)pl->p.M * pl->p.N;
   if (pl->fin_mode == 1) {
-    skinny_finalize_norm_kernel<<<pl->p.M * FIN_CL, 256, 0, st>>>(pl->p.partial, pl->p.R, pl->p.out, pl->norm_w, pl->aux, pl->p.M, pl->p.N,
-                                                         pl->p.splits, pl->eps, pl->kyutai);
+    launch_pdl(skinny_finalize_norm_kernel, dim3(pl->p.M * FIN_CL), dim3(256), 0, st, (const float*)pl->p.partial, pl->p.R, pl->p.out, pl->norm_w,
+               pl->aux, pl->p.M, pl->p.N, pl->p.splits, pl->eps, pl->kyutai);
     count_launch();
     return check_launch("skinny_finalize_norm");
   }
   if (pl->fin_mode == 2) {
     int g = ceil_div(MN / 2, 256);
     if (g > 148 * 8) g = 148 * 8;
-    skinny_finalize_silu_kernel<<<g, 256, 0, st>>>(pl->p.partial, pl->aux, pl->p.M, pl->p.N, pl->p.splits);
+    launch_pdl(skinny_finalize_silu_kernel, dim3(g), dim3(256), 0, st, (const float*)pl->p.partial, pl->aux, pl->p.M, pl->p.N, pl->p.splits);
     count_launch();
     return check_launch("skinny_finalize_silu");
   }
   if (pl->p.splits > 1) {
     int g = ceil_div(MN / 4, 256);
     if (g > 148 * 4) g = 148 * 4;
-    skinny_finalize_kernel<<<g, 256, 0, st>>>(pl->p.partial, pl->p.R, pl->p.out, MN, pl->p.splits);
+    launch_pdl(skinny_finalize_kernel, dim3(g), dim3(256), 0, st, (const float*)pl->p.partial, pl->p.R, pl->p.out, MN, pl->p.splits);
     count_launch();
     return check_launch("skinny_finalize");
   }

@@ -31,6 +31,8 @@ __device__ __forceinline__ bf16 f2b(float v) { return __float2bfloat16(v); }
 __global__ void embed_sum_kernel(const long long* __restrict__ seq, int seq_stride, const bf16* __restrict__ wte,
                                  const bf16* const* __restrict__ tables, int n_q, int E, bf16* __restrict__ x,
                                  long long wte_rows, long long table_rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const long long* ids = seq + (long long)b * seq_stride;
   bool bad = ids[0] < -1 || ids[0] >= wte_rows;
@@ -56,6 +58,8 @@ __global__ void embed_sum_kernel(const long long* __restrict__ seq, int seq_stri
 // out[b] = table[id[b]] (zero row for id < 0): depth-transformer token embeddings (llama_streaming.py:738-742)
 __global__ void embed_rows_kernel(const long long* __restrict__ ids, int id_stride, const bf16* __restrict__ table, int D,
                                   bf16* __restrict__ out, long long rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const long long id = ids[(long long)b * id_stride];
   const bool bad = id < -1 || id >= rows;
@@ -68,6 +72,8 @@ __global__ void embed_rows_kernel(const long long* __restrict__ ids, int id_stri
 // kyutai variant modules/transformer.py:34-48: var = eps + mean(x^2); y = x * (alpha * rsqrt(var)))
 __global__ void rms_norm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, bf16* __restrict__ y, int dim, float eps,
                                 int kyutai) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[32];
   const int b = blockIdx.x;
   const bf16* xr = x + (long long)b * dim;
@@ -103,6 +109,8 @@ __global__ void rope_kv_append_bf16_kernel(const bf16* __restrict__ qkv, const b
                                            const long long* __restrict__ offset, bf16* __restrict__ q_out, bf16* __restrict__ kv,
                                            int ostride, int B, int n_kv, int q_per_kv, int hs, int cap, int rope_n,
                                            long long rope_rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x / n_kv, g = blockIdx.x % n_kv;
   const int b = row % B;
   const long long pos = offset[(long long)b * ostride] + row / B;   // per-stream counters (ostride 1) or one shared (0)
@@ -144,6 +152,8 @@ __global__ void rope_kv_append_bf16_kernel(const bf16* __restrict__ qkv, const b
 __global__ void rope_pair_kv_append_bf16_kernel(const bf16* __restrict__ qkv, const long long* __restrict__ offset, int ostride,
                                                 bf16* __restrict__ q_out, bf16* __restrict__ kv, int B, int H, int hd, int cap,
                                                 const float* __restrict__ freqs) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x / H, h = blockIdx.x % H;
   const int b = row % B;
   const long long off = offset[(long long)b * ostride];
@@ -182,6 +192,8 @@ __global__ void __launch_bounds__(256, (G == 1 ? 3 : 2)) ring_decode_attention_k
                                                                     const long long* __restrict__ offset, bf16* __restrict__ out,
                                                                     int ostride, int B, int nh, int n_kv, int cap, int context,
                                                                     float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int DPL = HS / 8;  // dims per lane
   const int h0 = blockIdx.x * G, row = blockIdx.y;
   const int b = row % B;
@@ -306,6 +318,8 @@ __global__ void __launch_bounds__(256, (G == 1 ? 3 : 2)) ring_decode_attention_k
 // ---------------------------------------------------------------- SiLU gating: out = silu(a) * b  (bf16 roundings as eager)
 // ab [M][2*I] with a = cols [0,I), b = cols [I,2I) (fused fc_1|fc_2, or gating's view(B,T,2,-1), gating.py:16-19)
 __global__ void silu_mul_kernel(const bf16* __restrict__ ab, bf16* __restrict__ out, int M, int I) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = (long long)M * I;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long m = i / I, c = i % I;
@@ -321,6 +335,8 @@ __global__ void silu_mul_kernel(const bf16* __restrict__ ab, bf16* __restrict__ 
 // (forward_codecformer); 0: the non-streaming form (forward_local: KVCacheResult.from_kv keeps every key).
 __global__ void depth_attention_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kvd, bf16* __restrict__ out, int B, int H,
                                        int hd, int cap, int step, int ring_quirk) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int lane = threadIdx.x;
   const int HD = H * hd;
@@ -358,6 +374,8 @@ __global__ void depth_attention_kernel(const bf16* __restrict__ qkv, bf16* __res
 
 __global__ void sample_kernel(const bf16* __restrict__ logits, int V, int n_valid, int top_k, float temp, uint32_t seed,
                               const long long* __restrict__ step_counter, long long* __restrict__ tokens, int tok_stride) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x;
   const uint32_t stepc = step_counter ? (uint32_t)(*step_counter) : 0u;
   sample_row(logits + (long long)row * V, n_valid, top_k, temp, seed, stepc, row, tokens + (long long)row * tok_stride);
@@ -370,8 +388,8 @@ extern "C" int rstnet_lm_embed_sum_bf16(const int64_t* seq, int32_t seq_stride, 
                                         const void* const* tables_dev, int64_t table_rows, int32_t n_q, int32_t E, void* x,
                                         int32_t rows, rstnet_stream_t stream) {
   RSTNET_REQUIRE(seq && wte && tables_dev && x && rows > 0 && wte_rows > 0 && table_rows > 0, "lm_embed_sum: bad argument");
-  embed_sum_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>((const long long*)seq, seq_stride, (const bf16*)wte,
-                                                           (const bf16* const*)tables_dev, n_q, E, (bf16*)x, wte_rows, table_rows);
+  launch_pdl(embed_sum_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, (const long long*)seq, seq_stride, (const bf16*)wte,
+             (const bf16* const*)tables_dev, n_q, E, (bf16*)x, (long long)wte_rows, (long long)table_rows);
   count_launch();
   return check_launch("lm_embed_sum");
 }
@@ -379,8 +397,8 @@ extern "C" int rstnet_lm_embed_sum_bf16(const int64_t* seq, int32_t seq_stride, 
 extern "C" int rstnet_lm_embed_rows_bf16(const int64_t* ids, int32_t id_stride, const void* table, int64_t table_rows, int32_t D,
                                          void* out, int32_t rows, rstnet_stream_t stream) {
   RSTNET_REQUIRE(ids && table && out && rows > 0 && table_rows > 0, "lm_embed_rows: bad argument");
-  embed_rows_kernel<<<rows, 128, 0, (cudaStream_t)stream>>>((const long long*)ids, id_stride, (const bf16*)table, D, (bf16*)out,
-                                                            table_rows);
+  launch_pdl(embed_rows_kernel, dim3(rows), dim3(128), 0, (cudaStream_t)stream, (const long long*)ids, id_stride, (const bf16*)table, D,
+             (bf16*)out, (long long)table_rows);
   count_launch();
   return check_launch("lm_embed_rows");
 }
@@ -388,7 +406,7 @@ extern "C" int rstnet_lm_embed_rows_bf16(const int64_t* ids, int32_t id_stride, 
 extern "C" int rstnet_lm_rms_norm_bf16(const void* x, const void* w, void* y, int32_t rows, int32_t dim, float eps, int32_t kyutai,
                                        rstnet_stream_t stream) {
   RSTNET_REQUIRE(x && w && y && rows > 0 && dim > 0, "lm_rms_norm: bad argument");
-  rms_norm_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)w, (bf16*)y, dim, eps, kyutai);
+  launch_pdl(rms_norm_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, (const bf16*)w, (bf16*)y, dim, eps, kyutai);
   count_launch();
   return check_launch("lm_rms_norm");
 }
@@ -401,10 +419,9 @@ extern "C" int rstnet_lm_rope_kv_append_bf16(const void* qkv, const void* cos_ta
   RSTNET_REQUIRE(rows > 0 && B > 0 && rows % B == 0, "lm_rope_kv_append: rows (%d) must be a multiple of the stream count (%d)", rows, B);
   RSTNET_REQUIRE(n_kv > 0 && n_head % n_kv == 0, "lm_rope_kv_append: n_head (%d) must be a multiple of n_kv (%d)", n_head, n_kv);
   RSTNET_REQUIRE(rope_n >= 0 && rope_n <= hs && rope_n % 2 == 0 && rope_rows > 0, "lm_rope_kv_append: bad rope table (%d of %d dims)", rope_n, hs);
-  rope_kv_append_bf16_kernel<<<rows * n_kv, 64, 0, (cudaStream_t)stream>>>((const bf16*)qkv, (const bf16*)cos_tab, (const bf16*)sin_tab,
-                                                                           (const long long*)offset, (bf16*)q_out, (bf16*)kv,
-                                                                           offset_stride ? 1 : 0, B, n_kv, n_head / n_kv, hs, cap,
-                                                                           rope_n, rope_rows);
+  launch_pdl(rope_kv_append_bf16_kernel, dim3(rows * n_kv), dim3(64), 0, (cudaStream_t)stream, (const bf16*)qkv, (const bf16*)cos_tab,
+             (const bf16*)sin_tab, (const long long*)offset, (bf16*)q_out, (bf16*)kv, offset_stride ? 1 : 0, B, n_kv, n_head / n_kv, hs,
+             cap, rope_n, (long long)rope_rows);
   count_launch();
   return check_launch("lm_rope_kv_append");
 }
@@ -414,9 +431,8 @@ extern "C" int rstnet_lm_rope_pair_kv_append_bf16(const void* qkv, const int64_t
                                                   rstnet_stream_t stream) {
   RSTNET_REQUIRE(qkv && offset && q_out && kv && freqs, "lm_rope_pair_kv_append: null pointer");
   RSTNET_REQUIRE(rows > 0 && B > 0 && rows % B == 0 && H > 0 && hd > 0 && hd % 2 == 0 && cap > 0, "lm_rope_pair_kv_append: bad shape");
-  rope_pair_kv_append_bf16_kernel<<<rows * H, 64, 0, (cudaStream_t)stream>>>((const bf16*)qkv, (const long long*)offset,
-                                                                             offset_stride ? 1 : 0, (bf16*)q_out, (bf16*)kv, B, H, hd,
-                                                                             cap, freqs);
+  launch_pdl(rope_pair_kv_append_bf16_kernel, dim3(rows * H), dim3(64), 0, (cudaStream_t)stream, (const bf16*)qkv,
+             (const long long*)offset, offset_stride ? 1 : 0, (bf16*)q_out, (bf16*)kv, B, H, hd, cap, freqs);
   count_launch();
   return check_launch("lm_rope_pair_kv_append");
 }
@@ -433,9 +449,9 @@ extern "C" int rstnet_lm_ring_decode_attention_bf16(const void* q, const void* k
   const int G = q_per_kv % 2 == 0 ? 2 : 1;   // query heads per CTA sharing the K/V rows (the rest of a group hits L2)
   dim3 grid(n_head / G, rows);
   cudaStream_t st = (cudaStream_t)stream;
-#define RSTNET_ATTN(HS_, G_)                                                                                               \
-  ring_decode_attention_kernel<HS_, G_><<<grid, 256, 0, st>>>((const bf16*)q, (const bf16*)kv, (const long long*)offset, \
-                                                               (bf16*)out, offset_stride ? 1 : 0, B, n_head, n_kv, cap, context, scale)
+#define RSTNET_ATTN(HS_, G_)                                                                                                  \
+  launch_pdl(ring_decode_attention_kernel<HS_, G_>, grid, dim3(256), 0, st, (const bf16*)q, (const bf16*)kv, (const long long*)offset, \
+             (bf16*)out, offset_stride ? 1 : 0, B, n_head, n_kv, cap, context, scale)
   if (hs == 128) { if (G == 2) RSTNET_ATTN(128, 2); else RSTNET_ATTN(128, 1); }
   else           { if (G == 2) RSTNET_ATTN(64, 2); else RSTNET_ATTN(64, 1); }
 #undef RSTNET_ATTN
@@ -448,7 +464,7 @@ extern "C" int rstnet_lm_silu_mul_bf16(const void* ab, void* out, int32_t M, int
   const long long total = (long long)M * I;
   int g = ceil_div(total, 256);
   if (g > 148 * 8) g = 148 * 8;
-  silu_mul_kernel<<<g, 256, 0, (cudaStream_t)stream>>>((const bf16*)ab, (bf16*)out, M, I);
+  launch_pdl(silu_mul_kernel, dim3(g), dim3(256), 0, (cudaStream_t)stream, (const bf16*)ab, (bf16*)out, M, I);
   count_launch();
   return check_launch("lm_silu_mul");
 }
@@ -457,7 +473,8 @@ extern "C" int rstnet_lm_depth_attention_bf16(const void* qkv, void* kvd, void* 
                                               int32_t step, int32_t ring_quirk, rstnet_stream_t stream) {
   RSTNET_REQUIRE(qkv && kvd && out, "lm_depth_attention: null pointer");
   RSTNET_REQUIRE(step >= 0 && step < cap && cap <= 8, "lm_depth_attention: step %d / capacity %d (<= 8) out of range", step, cap);
-  depth_attention_kernel<<<B * H, 32, 0, (cudaStream_t)stream>>>((const bf16*)qkv, (bf16*)kvd, (bf16*)out, B, H, hd, cap, step, ring_quirk);
+  launch_pdl(depth_attention_kernel, dim3(B * H), dim3(32), 0, (cudaStream_t)stream, (const bf16*)qkv, (bf16*)kvd, (bf16*)out, B, H, hd, cap,
+             step, ring_quirk);
   count_launch();
   return check_launch("lm_depth_attention");
 }
@@ -469,8 +486,8 @@ extern "C" int rstnet_lm_sample_bf16(const void* logits, int32_t rows, int32_t V
   RSTNET_REQUIRE(top_k <= SAMPLE_CAND && (top_k == 0 || temp > 0.f), "lm_sample: top_k <= %d and temp > 0 required (top_k=%d)", SAMPLE_CAND, top_k);
   if (n_valid <= 0 || n_valid > V) n_valid = V;
   if (top_k > n_valid) top_k = n_valid;   // torch.topk would raise; the whole support is the natural reading
-  sample_kernel<<<rows, 1024, 0, (cudaStream_t)stream>>>((const bf16*)logits, V, n_valid, top_k, temp, seed,
-                                                         (const long long*)step_counter, (long long*)tokens, tok_stride);
+  launch_pdl(sample_kernel, dim3(rows), dim3(1024), 0, (cudaStream_t)stream, (const bf16*)logits, V, n_valid, top_k, temp, (uint32_t)seed,
+             (const long long*)step_counter, (long long*)tokens, tok_stride);
   count_launch();
   return check_launch("lm_sample");
 }
