@@ -18,7 +18,7 @@ else:  # conv in time-major layout: B Cin Cout k s T pre
     nk = k * Cin // 32
 gx, gy, bn = C.c_int32(), C.c_int32(), C.c_int32()
 _lib.lib().rstnet_tc_gemm_grid(plan._h, C.byref(gx), C.byref(gy), C.byref(bn))
-trace = torch.zeros(nk, 8, dtype=torch.int64, device="cuda")
+trace = torch.zeros(max(nk, 8), 8, dtype=torch.int64, device="cuda")
 ct = torch.zeros(max(gx.value, 148), 4, dtype=torch.int64, device="cuda")
 for _ in range(3): plan.run()
 _lib.lib().rstnet_tc_gemm_set_trace(plan._h, trace.data_ptr(), ct.data_ptr())
@@ -34,7 +34,7 @@ print(f"CTA lifetime ns: mean {life.mean():.0f} min {life.min():.0f} max {life.m
       f"main {(c[:,2]-c[:,1]).float().mean():.0f} ns; all CTAs span {int(c[:,3].max()) - g0} ns")
 order = torch.argsort(c[:, 0])
 print("first CTA starts (ns):", [int(c[i, 0]) - g0 for i in order[:4]], " 149th..:", "")
-print("epilogue stamps (end, pre-bar, post-bar, staged, p0 phase1 done, p0 stored, p1 phase1, p1 stored):", [int(t[k,7]) - t0 for k in range(8)])
+print("epilogue stamps (end, pre-bar, post-bar, staged, p0 phase1 done, p0 stored, p1 phase1, p1 stored):", [int(t[k, 7]) - t0 for k in range(8)])
 print("kit  prod  landed  xformed  mma_start mma_issued | drain_b drain_e")
 for k in range(min(nk, 16)):
     r = [int(v) - t0 if int(v) else -1 for v in t[k]]
