@@ -659,7 +659,7 @@ def cfg5_duplex_bench(dev, S, ticks: int = 40):
             res["runs"].append({"streams": B, "error": "out of memory (KV rings)"})
         lm._state = None
         codec._stream_state = None
-        eng = sch = None
+        eng = sch = st = plan = kv = out = None      # every local that still points into the scope's HBM
         gc.collect()
         torch.cuda.empty_cache()
     ok = [r["streams"] for r in res["runs"] if r.get("realtime")]
