@@ -310,8 +310,12 @@ struct TsCfg {
   static constexpr int ACC_COLS = 2 * TC_NACC * BN;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// DW = drain / epilogue warps: 4 (each thread finishes a whole BN-wide row) or 8 (two warps share a TMEM lane quarter and
+// split the columns).  A short-K tile (the 24 kHz / 6 kHz resblock convs: 1..8 stages) is bound by its epilogue -- bias,
+// residual, ELU, swizzled staging of 128 x BN outputs -- which four warps run at ~4 650 clk per 128x64 tile against
+// <= 2 000 clk of main loop; eight warps halve it.  Long-K tiles keep DW = 4 (448 threads, 128 registers).
+template <int BN, int DW>
+__global__ void __launch_bounds__(320 + 32 * DW, 1)
 gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW3,
                   const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
                   const __grid_constant__ CUtensorMap tmR, const TcParams p) {
@@ -358,7 +362,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (p.tma_store) { tma_prefetch_desc(&tmC); if (p.C2) tma_prefetch_desc(&tmC2); if (p.R) tma_prefetch_desc(&tmR); }
     for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < TS_NA; ++s) { mbar_init(&a_ready[s], 128); mbar_init(&a_free[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 32 * DW); }
     mbar_init(r_full, 1);
     fence_barrier_init();
   }
@@ -511,6 +515,9 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else {
     const int q = warp % 4, dt = threadIdx.x - 320;
     const int row = q * 32 + lane;
+    constexpr int NDT = 32 * DW;             // drain threads
+    constexpr int CW = BN / (DW / 4);        // columns finished by one drain thread
+    const int cbeg = ((warp - 10) / 4) * CW; // this warp's column range [cbeg, cbeg + CW) of the tile
     int cc = 0;
     for (int ti = 0; ti < my_tiles; ++ti) {
       const int t = blockIdx.x + ti * gridDim.x;
@@ -539,18 +546,18 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
       }
-      float acc[BN];
+      float acc[CW];
 #pragma unroll
-      for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+      for (int j = 0; j < CW; ++j) acc[j] = 0.f;
       for (int chunk = 0; chunk < nchunks; ++chunk, ++cc) {
         const int buf = cc & 1;
         mbar_wait(&acc_full[buf], (cc >> 1) & 1);
         tc_fence_after();
         if (tr && ti == tr_ti && threadIdx.x == 320) p.trace[chunk * 8 + 5] = clock64();
 #pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 16) {
+        for (int c0 = 0; c0 < CW; c0 += 16) {
           uint32_t r[16], r2[16];
-          const uint32_t col = (uint32_t)(buf * TC_NACC * BN + c0);
+          const uint32_t col = (uint32_t)(buf * TC_NACC * BN + cbeg + c0);
           tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + col, r);
           tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + col + (uint32_t)BN, r2);
           tmem_ld_wait();
@@ -563,7 +570,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       const bool etr = tr && ti == tr_ti && threadIdx.x == 320;
       if (etr) p.trace[1 * 8 + 7] = clock64();
-      named_bar_sync(1, 128);   // bias/scale of this tile are in smem (written before the chunk loop)
+      named_bar_sync(1, NDT);   // bias/scale of this tile are in smem (written before the chunk loop)
       if (etr) p.trace[2 * 8 + 7] = clock64();
       if (p.tma_store) {
         // Epilogue without per-thread global stores: the row (thread = TMEM lane) is finished in registers, written
@@ -579,24 +586,22 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           uint8_t* boxes = reinterpret_cast<uint8_t*>(out_stage) + ((p.R ? (ti & 1) : oi) ? Cfg::BOXSET_BYTES : 0);
           if (!p.R && oi == 0) {
             if (dt == 0) bulk_wait_read0();             // the previous tile's stores no longer read either box set
-            named_bar_sync(2, 128);
+            named_bar_sync(2, NDT);
           }
           auto stage_rows = [&](auto act_c, auto res_c) {   // one instantiation per activation: only the executed one is fetched
             constexpr int ACTC = decltype(act_c)::value;
             constexpr bool RES = decltype(res_c)::value;
 #pragma unroll
-            for (int g8 = 0; g8 < BN / 32; ++g8) {
-              uint8_t* bx = boxes + g8 * (TC_BM * 128) + rsw;
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const int c = g8 * 32 + 4 * j;
-                const float4 bb = *reinterpret_cast<const float4*>(sb + c);
-                const float4 ss = *reinterpret_cast<const float4*>(sb + BN + c);
-                float4 v = make_float4((acc[c] + bb.x) * ss.x, (acc[c + 1] + bb.y) * ss.y, (acc[c + 2] + bb.z) * ss.z, (acc[c + 3] + bb.w) * ss.w);
-                float4* slot = reinterpret_cast<float4*>(bx + (((uint32_t)j ^ rx) << 4));
-                if (RES) { const float4 rr = *slot; v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
-                *slot = apply_act4_tc<ACTC>(v);
-              }
+            for (int lc = 0; lc < CW; lc += 4) {          // register index static, box / slot from the runtime column
+              const int c = cbeg + lc;
+              uint8_t* bx = boxes + (c >> 5) * (TC_BM * 128) + rsw;
+              const uint32_t j = (uint32_t)((c & 31) >> 2);
+              const float4 bb = *reinterpret_cast<const float4*>(sb + c);
+              const float4 ss = *reinterpret_cast<const float4*>(sb + BN + c);
+              float4 v = make_float4((acc[lc] + bb.x) * ss.x, (acc[lc + 1] + bb.y) * ss.y, (acc[lc + 2] + bb.z) * ss.z, (acc[lc + 3] + bb.w) * ss.w);
+              float4* slot = reinterpret_cast<float4*>(bx + ((j ^ rx) << 4));
+              if (RES) { const float4 rr = *slot; v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
+              *slot = apply_act4_tc<ACTC>(v);
             }
           };
           if (p.R) {
@@ -607,7 +612,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           else if (act == ACT_GELU) stage_rows(std::integral_constant<int, ACT_GELU>{}, std::false_type{});
           else stage_rows(std::integral_constant<int, ACT_NONE>{}, std::false_type{});
           fence_proxy_async_smem();
-          named_bar_sync(3, 128);
+          named_bar_sync(3, NDT);
           if (dt == 0) {
             const CUtensorMap* tm = second ? &tmC2 : &tmC;
             for (int g8 = 0; g8 < BN / 32; ++g8) {
@@ -624,8 +629,9 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (tr && ti == tr_ti && threadIdx.x == 320) p.trace[7] = clock64();
         continue;
       }
+      if constexpr (DW == 4) {
       // transpose through shared memory: thread = row while draining TMEM, 8 lanes = one 128-byte row segment when
-      // storing, so every global access is a full line
+      // storing, so every global access is a full line (plans whose output cannot be a TMA tile store; DW == 4 only)
       constexpr int LD = Cfg::OUT_LD;
       float* stg = out_stage + q * 32 * LD;
       __syncwarp();
@@ -688,6 +694,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
       if (tr && ti == tr_ti && threadIdx.x == 320) p.trace[7] = clock64();
+      }  // DW == 4
     }
   }
   if (threadIdx.x == 320) bulk_wait0();   // the issuing thread's TMA stores are complete before the CTA (and its smem) goes away
@@ -727,12 +734,12 @@ struct rstnet_tc_plan {
   int bn, prec;
 };
 
-template <int BN>
+template <int BN, int DW>
 static int tc_launch_ts(const rstnet_tc_plan* pl, cudaStream_t st) {
   using Cfg = TsCfg<BN>;
   static unsigned long long attr = 0;
-  smem_optin(gemm_tc_ts_kernel<BN>, Cfg::SMEM_BYTES, attr);
-  gemm_tc_ts_kernel<BN><<<pl->grid_ts, TC_THREADS, Cfg::SMEM_BYTES, st>>>(pl->tmA, pl->tmW3, pl->tmC, pl->tmC2, pl->tmR, pl->p);
+  smem_optin(gemm_tc_ts_kernel<BN, DW>, Cfg::SMEM_BYTES, attr);
+  gemm_tc_ts_kernel<BN, DW><<<pl->grid_ts, 320 + 32 * DW, Cfg::SMEM_BYTES, st>>>(pl->tmA, pl->tmW3, pl->tmC, pl->tmC2, pl->tmR, pl->p);
   count_launch();
   return check_launch("gemm_tc_ts");
 }
@@ -871,7 +878,14 @@ extern "C" int rstnet_tc_gemm_run(const rstnet_tc_plan* pl, rstnet_stream_t stre
   cudaStream_t st = (cudaStream_t)stream;
   if (pl->prec == 0) {
     static const bool use_ts = []() { const char* e = getenv("RSTNET_TC_SS"); return !(e && e[0] == '1'); }();
-    if (use_ts && pl->ts_ok) return pl->bn == 64 ? tc_launch_ts<64>(pl, st) : tc_launch_ts<32>(pl, st);
+    if (use_ts && pl->ts_ok) {
+      // eight drain warps for short-K tiles with a TMA-store epilogue (epilogue-bound); RSTNET_TC_DW=4 / 8 forces one
+      static const int force_dw = []() { const char* e = getenv("RSTNET_TC_DW"); return e ? atoi(e) : 0; }();
+      const int stages = pl->p.taps * pl->p.kchunks;
+      const bool dw8 = pl->p.tma_store && (force_dw == 8 || (force_dw != 4 && stages <= 8));
+      if (dw8) return pl->bn == 64 ? tc_launch_ts<64, 8>(pl, st) : tc_launch_ts<32, 8>(pl, st);
+      return pl->bn == 64 ? tc_launch_ts<64, 4>(pl, st) : tc_launch_ts<32, 4>(pl, st);
+    }
     if (pl->bn == 64) return tc_launch<64, 0>(pl, st);
     return tc_launch<32, 0>(pl, st);
   }
