@@ -310,10 +310,10 @@ struct TsCfg {
   static constexpr int ACC_COLS = 2 * TC_NACC * BN;
 };
 
-// DW = drain / epilogue warps: 4 (each thread finishes a whole BN-wide row) or 8 (two warps share a TMEM lane quarter and
-// split the columns).  A short-K tile (the 24 kHz / 6 kHz resblock convs: 1..8 stages) is bound by its epilogue -- bias,
-// residual, ELU, swizzled staging of 128 x BN outputs -- which four warps run at ~4 650 clk per 128x64 tile against
-// <= 2 000 clk of main loop; eight warps halve it.  Long-K tiles keep DW = 4 (448 threads, 128 registers).
+// DW = drain / epilogue warps: 4 (each thread finishes a whole BN-wide row; also the non-TMA-store fallback) or 8 (two
+// warps share a TMEM lane quarter and split the columns; 576 threads, 96 registers).  A short-K tile (the 24 kHz / 6 kHz
+// resblock convs: 1..8 stages) is bound by its epilogue -- promotion adds, bias, residual, ELU, swizzled staging of 128 x BN
+// outputs -- which four warps run at ~4 650 clk per 128x64 tile against <= 2 000 clk of main loop; eight warps halve it.
 template <int BN, int DW>
 __global__ void __launch_bounds__(320 + 32 * DW, 1)
 gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW3,
@@ -879,10 +879,12 @@ extern "C" int rstnet_tc_gemm_run(const rstnet_tc_plan* pl, rstnet_stream_t stre
   if (pl->prec == 0) {
     static const bool use_ts = []() { const char* e = getenv("RSTNET_TC_SS"); return !(e && e[0] == '1'); }();
     if (use_ts && pl->ts_ok) {
-      // eight drain warps for short-K tiles with a TMA-store epilogue (epilogue-bound); RSTNET_TC_DW=4 / 8 forces one
+      // eight drain warps whenever the epilogue is a TMA tile store (measured on the 256-stream codec pass: 63.6 k frames/s
+      // with four drain warps everywhere, 64.9 k with eight on tiles of <= 8 stages only, 68.5 k with eight everywhere:
+      // the drain of a long-K tile also gains more from twice the warps than it loses to 96 registers);
+      // RSTNET_TC_DW=4 restores the four-warp kernel
       static const int force_dw = []() { const char* e = getenv("RSTNET_TC_DW"); return e ? atoi(e) : 0; }();
-      const int stages = pl->p.taps * pl->p.kchunks;
-      const bool dw8 = pl->p.tma_store && (force_dw == 8 || (force_dw != 4 && stages <= 8));
+      const bool dw8 = pl->p.tma_store && force_dw != 4;
       if (dw8) return pl->bn == 64 ? tc_launch_ts<64, 8>(pl, st) : tc_launch_ts<32, 8>(pl, st);
       return pl->bn == 64 ? tc_launch_ts<64, 4>(pl, st) : tc_launch_ts<32, 4>(pl, st);
     }
