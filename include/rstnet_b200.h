@@ -276,10 +276,14 @@ int rstnet_lm_rope_pair_kv_append_bf16(const void* qkv, const int64_t* offset, i
 /* ---- one query position per row over the ring with RingKVCache.complete's position labels and the
  * (pos_k>=0)&(delta>=0)&(delta<context) mask (llama_streaming.py:983-992), fp32 softmax. HBM-bound.  Rows as above;
  * every position of the launch must already be in the ring and no slot a query needs may have been overwritten
- * (callers keep *offset + Tn <= cap for Tn > 1). */
+ * (callers keep *offset + Tn <= cap for Tn > 1).
+ * split_ws (optional, rstnet_lm_attention_split_workspace bytes, its first rows*n_head int32 zeroed ONCE by the caller): lets
+ * the kernel cut every job's keys in three chunks walked by persistent CTAs when rows * heads would otherwise leave a badly
+ * filled last wave; partials are combined in chunk order (deterministic). */
+int64_t rstnet_lm_attention_split_workspace(int32_t rows, int32_t n_head, int32_t hs);
 int rstnet_lm_ring_decode_attention_bf16(const void* q, const void* kv, const int64_t* offset, int32_t offset_stride,
                                          void* out, int32_t rows, int32_t B, int32_t n_head, int32_t n_kv, int32_t hs,
-                                         int32_t cap, int32_t context, rstnet_stream_t stream);
+                                         int32_t cap, int32_t context, void* split_ws, rstnet_stream_t stream);
 /* out[m][c] = silu(ab[m][c]) * ab[m][I + c]   (LLaMAMLP / ActivationGating) */
 int rstnet_lm_silu_mul_bf16(const void* ab, void* out, int32_t M, int32_t I, rstnet_stream_t stream);
 /* ---- depth transformer attention at codebook step `step` (keys 0..step, capacity dep_q <= 8, no RoPE):

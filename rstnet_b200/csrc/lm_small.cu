@@ -3,6 +3,7 @@
 // embedding gather, greedy / top-k sampling.  One token per stream (T == 1): rows are streams.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/rstnet_b200.h"
 
@@ -187,15 +188,30 @@ __global__ void rope_pair_kv_append_bf16_kernel(const bf16* __restrict__ qkv, co
 // Mask = RingKVCache.complete + (pos_k>=0)&(delta>=0)&(delta<context) (llama_streaming.py:983-992).
 // Row r = tl*B + b queries stream b at position *offset + tl; all positions of the launch are already in the ring
 // (the caller guarantees no slot a query still needs has been overwritten: see GPT.forward_global's prefill path).
-template <int HS, int G>
+// NS > 1 (key-split form): the work items are (row, head group, key chunk) triples walked by persistent CTAs
+// (item = blockIdx.x + i * gridDim.x), so the 2048 equal (stream, head) jobs of the 7B step no longer run as 4.6 waves of 444
+// resident CTAs (8 % of the kernel was an under-filled last wave) but as 13.8 rounds of thirds.  A chunk's unnormalised
+// (max, sum, acc[HS]) goes to `ws`; the CTA that completes a (row, head group) -- found with one atomic counter, reset for
+// the next launch -- combines the NS partials in chunk order, so the result does not depend on which CTA came last.
+// ST > 0: the K/V rows travel through a per-lane cp.async ring in shared memory, ST - 1 sweeps (of 32 keys per CTA) in
+// flight per warp instead of the one a register double buffer affords -- every lane copies and reads back only its own
+// 16-byte pieces, so cp.async.wait_group is the only synchronisation.
+template <int HS, int G, int NS, int ST>
 __global__ void __launch_bounds__(256, (G == 1 ? 3 : 2)) ring_decode_attention_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kv,
                                                                     const long long* __restrict__ offset, bf16* __restrict__ out,
                                                                     int ostride, int B, int nh, int n_kv, int cap, int context,
-                                                                    float scale) {
+                                                                    float scale, int rows, float* __restrict__ ws, int* __restrict__ arrive) {
   pdl_launch_dependents();
   pdl_wait();
   constexpr int DPL = HS / 8;  // dims per lane
-  const int h0 = blockIdx.x * G, row = blockIdx.y;
+  constexpr int PW = HS + 2;   // floats per partial: acc[HS], max, sum
+  __shared__ float sm_m[G][8], sm_l[G][8], sm_acc[G][8][HS];
+  __shared__ int sm_last;
+  const int nhg = nh / G;
+  const int n_items = rows * nhg * NS;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  const int split = item % NS, hg = (item / NS) % nhg, row = item / (NS * nhg);
+  const int h0 = hg * G;
   const int b = row % B;
   const int g = h0 / (nh / n_kv);
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -205,15 +221,22 @@ __global__ void __launch_bounds__(256, (G == 1 ? 3 : 2)) ring_decode_attention_k
   long long lo = pos - context + 1;
   if (lo < 0) lo = 0;
   if (lo < pos + 2 - cap) lo = pos + 2 - cap;  // ring quirk: the oldest slot is labelled end_offset and masked
-  const long long nkeys = pos - lo + 1;
+  const long long nkeys_all = pos - lo + 1;
+  const long long csz = NS == 1 ? nkeys_all : ((nkeys_all + NS - 1) / NS + 31) / 32 * 32;   // keys per chunk (whole 32-key sweeps)
+  lo += (long long)split * csz;
+  long long nkeys = nkeys_all - (long long)split * csz;
+  if (nkeys > csz) nkeys = csz;
+  if (nkeys < 0) nkeys = 0;
   const bf16* Kb = kv + ((long long)b * n_kv + g) * cap * HS;
   const bf16* Vb = Kb + (long long)B * n_kv * cap * HS;
   float qf[G][DPL];
 #pragma unroll
   for (int u = 0; u < G; ++u) {
-    const bf16* qp = q + ((long long)row * nh + h0 + u) * HS + sub * DPL;
+    // lane `sub` owns dims {p * 64 + sub * 8 + e}: piece p of all 8 lanes is one contiguous 128-byte run of a K/V row, so
+    // every load instruction asks for whole 32-byte sectors (cp.async.cg bypasses L1 and would otherwise fetch each twice)
+    const bf16* qp = q + ((long long)row * nh + h0 + u) * HS + sub * 8;
 #pragma unroll
-    for (int i = 0; i < DPL; ++i) qf[u][i] = b2f(qp[i]);
+    for (int i = 0; i < DPL; ++i) qf[u][i] = b2f(qp[(i / 8) * 64 + i % 8]);
   }
   float m[G], l[G], acc[G][DPL];
 #pragma unroll
@@ -222,22 +245,58 @@ __global__ void __launch_bounds__(256, (G == 1 ? 3 : 2)) ring_decode_attention_k
 #pragma unroll
     for (int i = 0; i < DPL; ++i) acc[u][i] = 0.f;
   }
-  // software pipeline: the K/V rows of the next iteration are in flight while this one is reduced
-  uint4 kr[DPL / 8], vr[DPL / 8], kn[DPL / 8], vn[DPL / 8];
+  // software pipeline: the K/V rows of the next iteration(s) are in flight while this one is reduced
+  constexpr int CH = DPL / 8;          // 16-byte pieces of a K (or V) row per lane
+  uint4 kr[CH], vr[CH], kn[ST > 0 ? 1 : CH], vn[ST > 0 ? 1 : CH];
+  extern __shared__ __align__(16) unsigned char attn_ring[];
+  uint4* ring = reinterpret_cast<uint4*>(attn_ring) + (ST > 0 ? warp * (ST * 2 * CH * 32) : 0);   // [stage][K pieces, V pieces][lane]
+  auto issue_rows = [&](long long j0, int s) {
+    const long long j = j0 + grp;
+    const int slot = (int)((lo + (j < nkeys ? j : 0)) % cap);
+    const uint4* kp = reinterpret_cast<const uint4*>(Kb + (long long)slot * HS) + sub;
+    const uint4* vp = reinterpret_cast<const uint4*>(Vb + (long long)slot * HS) + sub;
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+      cp_async16(&ring[(s * 2 * CH + i) * 32 + lane], kp + i * 8, 16);
+      cp_async16(&ring[(s * 2 * CH + CH + i) * 32 + lane], vp + i * 8, 16);
+    }
+  };
   auto load_rows = [&](long long j0, uint4* kd, uint4* vd) {
     const long long j = j0 + grp;
     const int slot = (int)((lo + (j < nkeys ? j : 0)) % cap);
-    const uint4* kp = reinterpret_cast<const uint4*>(Kb + (long long)slot * HS + sub * DPL);
-    const uint4* vp = reinterpret_cast<const uint4*>(Vb + (long long)slot * HS + sub * DPL);
+    const uint4* kp = reinterpret_cast<const uint4*>(Kb + (long long)slot * HS) + sub;
+    const uint4* vp = reinterpret_cast<const uint4*>(Vb + (long long)slot * HS) + sub;
 #pragma unroll
-    for (int i = 0; i < DPL / 8; ++i) { kd[i] = __ldg(kp + i); vd[i] = __ldg(vp + i); }
+    for (int i = 0; i < DPL / 8; ++i) { kd[i] = __ldg(kp + i * 8); vd[i] = __ldg(vp + i * 8); }
   };
   const long long jstep = (long long)nwarps * 4;
   long long j0 = (long long)warp * 4;
-  if (j0 < nkeys) load_rows(j0, kr, vr);
+  int stage = 0;
+  if constexpr (ST > 0) {
+#pragma unroll
+    for (int s = 0; s < ST - 1; ++s) {
+      if (j0 + s * jstep < nkeys) issue_rows(j0 + s * jstep, s);
+      cp_async_commit();
+    }
+  } else {
+    if (j0 < nkeys) load_rows(j0, kr, vr);
+  }
   for (; j0 < nkeys; j0 += jstep) {
     const bool more = j0 + jstep < nkeys;
-    if (more) load_rows(j0 + jstep, kn, vn);
+    if constexpr (ST > 0) {
+      const int sn = stage == 0 ? ST - 1 : stage - 1;       // the stage consumed in the previous iteration
+      if (j0 + (ST - 1) * jstep < nkeys) issue_rows(j0 + (ST - 1) * jstep, sn);
+      cp_async_commit();
+      cp_async_wait<ST - 1>();
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        kr[i] = ring[(stage * 2 * CH + i) * 32 + lane];
+        vr[i] = ring[(stage * 2 * CH + CH + i) * 32 + lane];
+      }
+      stage = stage + 1 == ST ? 0 : stage + 1;
+    } else {
+      if (more) load_rows(j0 + jstep, kn, vn);
+    }
     const bool valid = j0 + grp < nkeys;
     float dot[G];
 #pragma unroll
@@ -274,12 +333,14 @@ __global__ void __launch_bounds__(256, (G == 1 ? 3 : 2)) ring_decode_attention_k
         m[u] = m_new;
       }
     }
-    if (more) {
+    if constexpr (ST == 0) {
+      if (more) {
 #pragma unroll
-      for (int i = 0; i < DPL / 8; ++i) { kr[i] = kn[i]; vr[i] = vn[i]; }
+        for (int i = 0; i < DPL / 8; ++i) { kr[i] = kn[i]; vr[i] = vn[i]; }
+      }
     }
   }
-  __shared__ float sm_m[G][8], sm_l[G][8], sm_acc[G][8][HS];
+  if constexpr (ST > 0) cp_async_wait<0>();
 #pragma unroll
   for (int u = 0; u < G; ++u) {
     // combine the 4 key groups of the warp (lanes sub, sub+8, sub+16, sub+24 hold the same dims)
@@ -297,7 +358,7 @@ __global__ void __launch_bounds__(256, (G == 1 ? 3 : 2)) ring_decode_attention_k
     if (grp == 0) {
       if (sub == 0) { sm_m[u][warp] = mu; sm_l[u][warp] = lu; }
 #pragma unroll
-      for (int i = 0; i < DPL; ++i) sm_acc[u][warp][sub * DPL + i] = acc[u][i];
+      for (int i = 0; i < DPL; ++i) sm_acc[u][warp][(i / 8) * 64 + sub * 8 + i % 8] = acc[u][i];
     }
   }
   __syncthreads();
@@ -311,7 +372,45 @@ __global__ void __launch_bounds__(256, (G == 1 ? 3 : 2)) ring_decode_attention_k
       ll += sm_l[u][w] * c;
       a += sm_acc[u][w][d] * c;
     }
-    out[((long long)row * nh + h0 + u) * HS + d] = f2b(a / ll);
+    if (NS == 1) {
+      out[((long long)row * nh + h0 + u) * HS + d] = f2b(a / ll);
+    } else {
+      float* pw = ws + ((long long)item * G + u) * PW;
+      pw[d] = a;
+      if (d == 0) { pw[HS] = mm; pw[HS + 1] = ll; }
+    }
+  }
+  if (NS > 1) {
+    __threadfence();                 // this chunk's partial is visible before the arrival is counted
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int old = atomicAdd(&arrive[row * nhg + hg], 1);
+      sm_last = old == NS - 1;
+      if (sm_last) arrive[row * nhg + hg] = 0;      // ready for the next launch (all NS arrivals of this one are in)
+    }
+    __syncthreads();
+    if (sm_last) {
+      __threadfence();
+      const long long first = ((long long)(row * nhg + hg) * NS) * G;   // the NS partials of this (row, head group) are adjacent items
+      for (int idx = threadIdx.x; idx < G * HS; idx += blockDim.x) {
+        const int u = idx / HS, d = idx % HS;
+        float mm = -INFINITY;
+#pragma unroll
+        for (int sp = 0; sp < NS; ++sp) mm = fmaxf(mm, __ldcg(ws + (first + (long long)sp * G + u) * PW + HS));
+        float ll = 0.f, a = 0.f;
+#pragma unroll
+        for (int sp = 0; sp < NS; ++sp) {
+          const float* pw = ws + (first + (long long)sp * G + u) * PW;
+          const float ms = __ldcg(pw + HS);
+          const float c = ms == -INFINITY ? 0.f : __expf(ms - mm);
+          ll += __ldcg(pw + HS + 1) * c;
+          a += __ldcg(pw + d) * c;
+        }
+        out[((long long)row * nh + h0 + u) * HS + d] = f2b(a / ll);
+      }
+    }
+  }
+  __syncthreads();                   // the shared combine buffers are reused by the next item
   }
 }
 
@@ -437,9 +536,14 @@ extern "C" int rstnet_lm_rope_pair_kv_append_bf16(const void* qkv, const int64_t
   return check_launch("lm_rope_pair_kv_append");
 }
 
+extern "C" int64_t rstnet_lm_attention_split_workspace(int32_t rows, int32_t n_head, int32_t hs) {
+  // [rows * n_head] int32 arrival counters (zeroed by the caller once), then 3 partials of (hs + 2) floats per (row, head)
+  return (int64_t)rows * n_head * 4 + (int64_t)rows * n_head * 3 * (hs + 2) * 4;
+}
+
 extern "C" int rstnet_lm_ring_decode_attention_bf16(const void* q, const void* kv, const int64_t* offset, int32_t offset_stride,
                                                     void* out, int32_t rows, int32_t B, int32_t n_head, int32_t n_kv, int32_t hs,
-                                                    int32_t cap, int32_t context, rstnet_stream_t stream) {
+                                                    int32_t cap, int32_t context, void* split_ws, rstnet_stream_t stream) {
   RSTNET_REQUIRE(q && kv && offset && out, "lm_ring_decode_attention: null pointer");
   RSTNET_REQUIRE(hs == 128 || hs == 64, "lm_ring_decode_attention: head_size must be 64 or 128 (got %d)", hs);
   RSTNET_REQUIRE(rows > 0 && B > 0 && rows % B == 0, "lm_ring_decode_attention: rows (%d) must be a multiple of the stream count (%d)", rows, B);
@@ -447,11 +551,34 @@ extern "C" int rstnet_lm_ring_decode_attention_bf16(const void* q, const void* k
   const float scale = 1.0f / sqrtf((float)hs);
   const int q_per_kv = n_head / n_kv;
   const int G = q_per_kv % 2 == 0 ? 2 : 1;   // query heads per CTA sharing the K/V rows (the rest of a group hits L2)
-  dim3 grid(n_head / G, rows);
   cudaStream_t st = (cudaStream_t)stream;
-#define RSTNET_ATTN(HS_, G_)                                                                                                  \
-  launch_pdl(ring_decode_attention_kernel<HS_, G_>, grid, dim3(256), 0, st, (const bf16*)q, (const bf16*)kv, (const long long*)offset, \
-             (bf16*)out, offset_stride ? 1 : 0, B, n_head, n_kv, cap, context, scale)
+  static const int sms = []() { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
+  const int n_jobs = rows * (n_head / G);
+  int* arrive = (int*)split_ws;
+  float* ws = split_ws ? (float*)((char*)split_ws + (size_t)rows * n_head * 4) : nullptr;
+  // split the keys only when the jobs would leave a badly filled last wave of resident CTAs
+  const int resident = sms * (G == 1 ? 3 : 2);
+  // opt-in by passing split_ws (measured slower than one CTA per job at the 7B shapes): only when the jobs exceed one wave
+  const bool split = split_ws != nullptr && n_jobs > resident;
+  static const int ring_stages = []() { const char* e = getenv("RSTNET_ATTN_STAGES"); return e ? atoi(e) : 4; }();   // 0: register double buffer
+  const bool ring = ring_stages == 4 && !split;
+  const int ring_bytes = ring ? 4 * 8 * 32 * (hs / 64) * 2 * 16 : 0;   // stages x warps x lanes x (K, V pieces) x 16 B
+#define RSTNET_ATTN(HS_, G_)                                                                                                       \
+  do {                                                                                                                             \
+    if (split)                                                                                                                     \
+      launch_pdl(ring_decode_attention_kernel<HS_, G_, 3, 0>, dim3(resident), dim3(256), 0, st, (const bf16*)q, (const bf16*)kv,   \
+                 (const long long*)offset, (bf16*)out, offset_stride ? 1 : 0, B, n_head, n_kv, cap, context, scale, rows, ws, arrive); \
+    else if (ring) {                                                                                                               \
+      static unsigned long long attr = 0;                                                                                          \
+      smem_optin(ring_decode_attention_kernel<HS_, G_, 1, 4>, ring_bytes, attr);                                                   \
+      launch_pdl(ring_decode_attention_kernel<HS_, G_, 1, 4>, dim3(n_jobs), dim3(256), ring_bytes, st, (const bf16*)q,             \
+                 (const bf16*)kv, (const long long*)offset, (bf16*)out, offset_stride ? 1 : 0, B, n_head, n_kv, cap, context,      \
+                 scale, rows, (float*)nullptr, (int*)nullptr);                                                                     \
+    } else                                                                                                                         \
+      launch_pdl(ring_decode_attention_kernel<HS_, G_, 1, 0>, dim3(n_jobs), dim3(256), 0, st, (const bf16*)q, (const bf16*)kv,     \
+                 (const long long*)offset, (bf16*)out, offset_stride ? 1 : 0, B, n_head, n_kv, cap, context, scale, rows,          \
+                 (float*)nullptr, (int*)nullptr);                                                                                  \
+  } while (0)
   if (hs == 128) { if (G == 2) RSTNET_ATTN(128, 2); else RSTNET_ATTN(128, 1); }
   else           { if (G == 2) RSTNET_ATTN(64, 2); else RSTNET_ATTN(64, 1); }
 #undef RSTNET_ATTN

@@ -237,6 +237,10 @@ class GPT(nn.Module):
         # 3.7 ms per frame at B = 64: the per-CTA activation-panel reads from L2 and the mma.sync dependency chains do not
         # overlap, and 264 grid barriers cost 0.55 ms by themselves -- DESIGN.md §6), so it is opt-in.
         self.use_depth_frame_kernel = False
+        # True: the temporal attention cuts every (stream, head) job's keys in three chunks walked by persistent CTAs
+        # (csrc/lm_small.cu).  Removes the under-filled last wave but pays the per-job prologue/combine three times:
+        # measured 491 us vs 430 us per layer at B = 64 x 32 heads x 2047 keys, so it is opt-in.
+        self.attention_key_split = False
 
     # parameter names of the depth transformer (the Moshi-style LMModel of rstnet_b200/moshi.py has the same structure under
     # other names, models/model.py:188-224)
@@ -505,6 +509,12 @@ class GPT(nn.Module):
         raise NotImplementedError("training / teacher-forcing forward is out of scope; use forward_global / forward_local")
 
 
+def _attention_split_workspace(rows: int, n_head: int, hs: int, dev) -> torch.Tensor:
+    """Scratch of the key-split attention form (include/rstnet_b200.h): arrival counters (zero between launches) + partials."""
+    n = _lib.lib().rstnet_lm_attention_split_workspace(rows, n_head, hs)
+    return torch.zeros(n, dtype=torch.uint8, device=dev)
+
+
 class _LMState:
     """Buffers, KV rings, GEMM plans of one `streaming(B)` scope.  Rows of every activation buffer are (position,
     stream) pairs, position-major: row = tl * B + b.  The decode state has tn == 1; a prefill chunk state (`parent` set)
@@ -618,6 +628,7 @@ class _LMState:
         nh, nkv, hs = c.n_head, c.n_query_groups, c.head_size
         self.seq = z(M, c.n_q + 1, dtype=torch.int64)
         self.x, self.xn, self.q, self.att = z(M, E), z(M, E), z(M, nh * hs), z(M, nh * hs)
+        self.att_ws = _attention_split_workspace(M, nh, hs, dev) if m.attention_key_split else None
         self.qkv, self.hmid = z(M, (nh + 2 * nkv) * hs), z(M, I)
         self.out, self.logits = z(M, E), z(M, V)
         if parent is None:
@@ -750,7 +761,7 @@ class _LMState:
                        "rope_kv")
             _lib.check(L.rstnet_lm_ring_decode_attention_bf16(self.q.data_ptr(), self.kv[l].data_ptr(), self.offset.data_ptr(), ost,
                                                               self.att.data_ptr(), M, B, c.n_head, c.n_query_groups, c.head_size,
-                                                              self.cap, c.context, st), "attention")
+                                                              self.cap, c.context, None if self.att_ws is None else self.att_ws.data_ptr(), st), "attention")
             ly["proj"].run()   # + residual + norm_2 -> xn
             ly["fc"].run()     # + SiLU gating -> hmid
             ly["down"].run()   # + residual + next pre-norm -> xn (last layer: ln_f -> transformer_out)

@@ -96,7 +96,7 @@ class _MoshiState(_LMState):
                                                             self.freqs.data_ptr(), st), "rope_pair_kv")
             _lib.check(L.rstnet_lm_ring_decode_attention_bf16(self.q.data_ptr(), self.kv[l].data_ptr(), self.offset.data_ptr(), 1,
                                                               self.att.data_ptr(), M, B, c.n_head, c.n_head, c.head_size, self.cap,
-                                                              c.context, st), "attention")
+                                                              c.context, None, st), "attention")
             ly["proj"].run()
             ly["fc"].run()
             ly["down"].run()

@@ -79,7 +79,7 @@ def test_rope_append_and_ring_decode_attention(hs, cap, context, steps):
         _lib.check(lib.rstnet_lm_rope_kv_append_bf16(qkv_d.data_ptr(), cos_d.data_ptr(), sin_d.data_ptr(), cos_d.shape[0], hs,
                                                      offset.data_ptr(), 0, qd.data_ptr(), kv.data_ptr(), B, B, nh, nh, hs, cap, st))
         _lib.check(lib.rstnet_lm_ring_decode_attention_bf16(qd.data_ptr(), kv.data_ptr(), offset.data_ptr(), 0, out.data_ptr(), B, B,
-                                                            nh, nh, hs, cap, context, st))
+                                                            nh, nh, hs, cap, context, None, st))
         ops.counter_add(offset, 1)
         torch.cuda.synchronize()
         assert torch.equal(qd.cpu().view(B, nh, hs), qr[:, :, 0]), "rotated q must match bit for bit"
@@ -496,27 +496,45 @@ def test_cfg3_shape_wrapped_ring_vs_reference_eager_on_gpu():
                 assert _rel(a, b_) <= 2e-2
 
 
-def test_attention_full_window_2047_keys_vs_sdpa():
+@pytest.mark.parametrize("B,split", [(4, False), (64, False), (64, True), (37, True)])
+def test_attention_full_window_2047_keys_vs_sdpa(B, split):
     """ring_decode_attention at head 128, capacity 2048, wrapped: vs SDPA over exactly the keys RingKVCache.complete
-    leaves attendable (MHA and a GQA grouping)."""
+    leaves attendable (MHA and a GQA grouping).  `split`: the persistent key-split form (taken when rows x heads exceed
+    the resident CTAs) -- must agree with the one-CTA-per-job form to bf16 rounding and be run-to-run deterministic;
+    streams at different fill levels (few keys, partially filled ring, wrapped) exercise empty key chunks."""
     lib, st_ = _lib.lib(), ops._stream()
-    B, hs, cap = 4, 128, 2048
+    hs, cap = 128, 2048
     g = torch.Generator().manual_seed(9)
-    for nh, nkv in ((8, 8), (8, 2)):
+    for nh, nkv in ((8, 8), (16, 4)):
         kv = torch.randn(2, B, nkv, cap, hs, generator=g).to(BF).to(DEV)
         q = torch.randn(B, nh, hs, generator=g).to(BF).to(DEV)
-        pos = cap + 100                                         # the query's own key sits at slot pos % cap
-        offset = torch.full((B,), pos, dtype=torch.int64, device=DEV)
+        pos_b = torch.full((B,), cap + 100, dtype=torch.int64)  # the query's own key sits at slot pos % cap
+        if B > 8:
+            pos_b[1], pos_b[2], pos_b[3], pos_b[4] = 0, 5, 40, 1000
+        offset = pos_b.to(DEV)
         out = torch.empty(B, nh * hs, dtype=BF, device=DEV)
-        _lib.check(lib.rstnet_lm_ring_decode_attention_bf16(q.data_ptr(), kv.data_ptr(), offset.data_ptr(), 1, out.data_ptr(), B, B,
-                                                            nh, nkv, hs, cap, cap, st_))
+        ws = torch.zeros(lib.rstnet_lm_attention_split_workspace(B, nh, hs), dtype=torch.uint8, device=DEV) if split else None
+        outs = []
+        for rep in range(2 if split else 1):
+            out.zero_()
+            _lib.check(lib.rstnet_lm_ring_decode_attention_bf16(q.data_ptr(), kv.data_ptr(), offset.data_ptr(), 1, out.data_ptr(), B, B,
+                                                                nh, nkv, hs, cap, cap, ws.data_ptr() if split else None, st_))
+            outs.append(out.clone())
+        if split:
+            assert torch.equal(outs[0], outs[1]), "key-split attention must be deterministic (and its counters self-resetting)"
+            assert int(ws[:B * nh * 4].view(torch.int32).abs().sum()) == 0
         slots = torch.arange(cap, device=DEV)
-        dead = (pos + 1) % cap                                  # labelled end_offset -> masked (the ring quirk)
-        mask = slots != dead
         k_, v_ = kv[0].float(), kv[1].float()
         rep = nh // nkv
         k_, v_ = k_.repeat_interleave(rep, 1), v_.repeat_interleave(rep, 1)
-        ref = F.scaled_dot_product_attention(q.float()[:, :, None], k_, v_, attn_mask=mask.view(1, 1, 1, cap), scale=1.0 / hs ** 0.5)[:, :, 0]
+        mask = torch.zeros(B, 1, 1, cap, dtype=torch.bool, device=DEV)
+        for b in range(B):
+            pos = int(pos_b[b])
+            if pos >= cap - 1:
+                mask[b, 0, 0] = slots != (pos + 1) % cap        # labelled end_offset -> masked (the ring quirk)
+            else:
+                mask[b, 0, 0] = slots <= pos
+        ref = F.scaled_dot_product_attention(q.float()[:, :, None], k_, v_, attn_mask=mask, scale=1.0 / hs ** 0.5)[:, :, 0]
         err = (out.float().view(B, nh, hs) - ref).abs().max().item()
         assert err <= 1.5e-2, (nh, nkv, err)
 
