@@ -39,7 +39,9 @@ template <int STAGES>
 __global__ void __launch_bounds__(SK_THREADS, 2)
 gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const SkParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment as pointer arithmetic on the __shared__ array (an integer round trip would demote every later
+  // access through `smem` to generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int x_bytes = p.MB * 128;
   const int stage_bytes = SK_W_BYTES + ((x_bytes + 1023) & ~1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);

@@ -82,7 +82,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto gtime = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (long long)t; };
   const bool timed = p.cta_times && blockIdx.y == 0 && threadIdx.x == 0;
   if (timed) p.cta_times[blockIdx.x * 4 + 0] = gtime();
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment as pointer arithmetic on the __shared__ array (an integer round trip would demote every later
+  // access through `smem` to generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::STAGE_BYTES);
   uint64_t* full = bars;               // [S] TMA landed
   uint64_t* ready = bars + S;          // [S] operands transformed (128 arrivals)
@@ -329,7 +331,9 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   constexpr int NV = S / (S % 4 == 0 ? 4 : (S % 2 == 0 ? 2 : 1));
   static_assert(((4 * NV / S) & 1) == 0, "stage parity must be static");
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment as pointer arithmetic on the __shared__ array (an integer round trip would demote every later
+  // access through `smem` to generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::STAGE_BYTES);
   uint64_t* full = bars;                         // [S] TMA landed (A fp32, [B_hi; B_lo])
   uint64_t* empty = bars + S;                    // [S] MMAs reading B of the stage retired (A smem was consumed earlier)
@@ -337,8 +341,8 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* a_free = bars + 2 * S + TS_NA;       // [NA] MMAs reading that TMEM stage retired
   uint64_t* acc_full = bars + 2 * S + 2 * TS_NA; // [2]
   uint64_t* acc_empty = acc_full + 2;            // [2] (128 arrivals)
-  uint64_t* r_full = acc_empty + 2;              // residual tile landed in the epilogue boxes
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(r_full + 1);
+  uint64_t* r_full = acc_empty + 2;              // [2] residual tile landed in the epilogue boxes (even / odd tiles of this CTA)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(r_full + 2);
   float* sbs = reinterpret_cast<float*>(smem + S * Cfg::STAGE_BYTES + 512);  // [2][2*BN] bias | scale of the drain's tile
   float* out_stage = reinterpret_cast<float*>(smem + S * Cfg::STAGE_BYTES + Cfg::CTRL_BYTES);   // epilogue staging (1024-aligned)
 
@@ -363,7 +367,8 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < TS_NA; ++s) { mbar_init(&a_ready[s], 128); mbar_init(&a_free[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 32 * DW); }
-    mbar_init(r_full, 1);
+    mbar_init(&r_full[0], 1);
+    mbar_init(&r_full[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_ptr);
@@ -526,26 +531,29 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       float* sb = sbs + (ti & 1) * 2 * BN;
       if (dt < BN) sb[dt] = (p.bias && n0 + dt < p.N) ? p.bias[n0 + dt] : 0.f;
       else if (dt < 2 * BN) sb[dt] = (p.scale && n0 + dt - BN < p.N) ? p.scale[n0 + dt - BN] : 1.f;
-      if (p.tma_store && p.R && dt == 0) {
-        // residual tile -> epilogue boxes while the K loop runs (the boxes are free once the previous store was read out)
-        // Residual layers alternate between two box sets: the residual of tile t+1 is requested right after the store of
-        // tile t was issued, and a load landing in the boxes that store is still reading corrupted the tail rows of tile t
-        // (seen rarely, on cold GPUs, on the 64->128 1x1 conv of the 6 kHz decoder level -- scripts/diag_rows.py).  The
-        // wait below then only has to cover the store of tile t-1.
-        bulk_wait_read0();
-        uint8_t* boxes = reinterpret_cast<uint8_t*>(out_stage) + (ti & 1) * Cfg::BOXSET_BYTES;
+      // Residual tile -> epilogue boxes by TMA.  Residual layers alternate between two box sets (and two mbarriers): the
+      // residual of tile t+1 is requested from the epilogue of tile t, as soon as the store of tile t-1 has been read out of
+      // the set it is going to land in, so its latency overlaps the staging and the store of tile t.  (A load landing in
+      // boxes a store is still reading corrupted the tail rows of a tile -- seen rarely, on cold GPUs, on the 64->128 1x1
+      // conv of the 6 kHz decoder level, scripts/diag_rows.py -- hence the read-out wait in front of every request.)
+      auto request_residual = [&](int tix) {
+        const int t2 = blockIdx.x + tix * gridDim.x;
+        const int nt2 = t2 % p.n_tiles, mt2 = t2 / p.n_tiles;
+        const int i2 = (mt2 % p.i_tiles) * TC_BM, ot2 = mt2 / p.i_tiles, n2 = nt2 * BN;
+        uint8_t* boxes = reinterpret_cast<uint8_t*>(out_stage) + (tix & 1) * Cfg::BOXSET_BYTES;
         int nb = 0;
-        for (int g8 = 0; g8 < BN / 32; ++g8) nb += (n0 + g8 * 32 < p.N) ? 1 : 0;
-        mbar_arrive_expect_tx(r_full, (uint32_t)(nb * TC_BM * 128));
+        for (int g8 = 0; g8 < BN / 32; ++g8) nb += (n2 + g8 * 32 < p.N) ? 1 : 0;
+        mbar_arrive_expect_tx(&r_full[tix & 1], (uint32_t)(nb * TC_BM * 128));
         for (int g8 = 0; g8 < BN / 32; ++g8) {
-          const int n = n0 + g8 * 32;
+          const int n = n2 + g8 * 32;
           if (n < p.N) {
-            int c0 = n, c2 = ot;
-            if (p.n_split > 0) { c0 = n % p.n_split; c2 = ot * p.c_tr + n / p.n_split; }
-            tma_load_3d(boxes + g8 * (TC_BM * 128), &tmR, r_full, c0, i0, c2);
+            int c0 = n, c2 = ot2;
+            if (p.n_split > 0) { c0 = n % p.n_split; c2 = ot2 * p.c_tr + n / p.n_split; }
+            tma_load_3d(boxes + g8 * (TC_BM * 128), &tmR, &r_full[tix & 1], c0, i2, c2);
           }
         }
-      }
+      };
+      if (p.tma_store && p.R && dt == 0 && ti == 0) request_residual(0);
       float acc[CW];
 #pragma unroll
       for (int j = 0; j < CW; ++j) acc[j] = 0.f;
@@ -554,6 +562,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         mbar_wait(&acc_full[buf], (cc >> 1) & 1);
         tc_fence_after();
         if (tr && ti == tr_ti && threadIdx.x == 320) p.trace[chunk * 8 + 5] = clock64();
+        if (tr && ti == tr_ti + 1 && chunk == 0 && threadIdx.x == 320) p.trace[7 * 8 + 7] = clock64();   // next tile's drain start: the tile period
 #pragma unroll
         for (int c0 = 0; c0 < CW; c0 += 16) {
           uint32_t r[16], r2[16];
@@ -583,11 +592,14 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const bool second = (nout == 2) && oi == 0;   // C2 first, C last
           const int act = second ? p.act2 : p.post_act;
           // [BN/32][128 rows][128 B] boxes, 1024-aligned; set 1 = odd tiles of residual layers / the second output of dual-output layers
-          uint8_t* boxes = reinterpret_cast<uint8_t*>(out_stage) + ((p.R ? (ti & 1) : oi) ? Cfg::BOXSET_BYTES : 0);
-          if (!p.R && oi == 0) {
-            if (dt == 0) bulk_wait_read0();             // the previous tile's stores no longer read either box set
+          // single-output layers alternate the two box sets per tile, dual-output layers per output: either way the set
+          // staged next was last read by the store before the most recent one, so ONE store may stay in flight
+          uint8_t* boxes = reinterpret_cast<uint8_t*>(out_stage) + (((p.R || nout == 1) ? (ti & 1) : oi) ? Cfg::BOXSET_BYTES : 0);
+          if (!p.R) {
+            if (dt == 0) bulk_wait_read1();
             named_bar_sync(2, NDT);
           }
+          if (etr) p.trace[3 * 8 + 7] = clock64();
           auto stage_rows = [&](auto act_c, auto res_c) {   // one instantiation per activation: only the executed one is fetched
             constexpr int ACTC = decltype(act_c)::value;
             constexpr bool RES = decltype(res_c)::value;
@@ -605,14 +617,22 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           };
           if (p.R) {
-            mbar_wait(r_full, (uint32_t)(ti & 1));   // one residual load per tile
+            mbar_wait(&r_full[ti & 1], (uint32_t)((ti >> 1) & 1));   // one residual load per tile
+            if (dt == 0 && ti + 1 < my_tiles) {
+              bulk_wait_read0();        // the store of tile ti-1 (issued a whole residual latency ago) has left the other set
+              request_residual(ti + 1);
+            }
+            if (etr) p.trace[3 * 8 + 7] = clock64();
             if (act == ACT_ELU) stage_rows(std::integral_constant<int, ACT_ELU>{}, std::true_type{});
             else stage_rows(std::integral_constant<int, ACT_NONE>{}, std::true_type{});
           } else if (act == ACT_ELU) stage_rows(std::integral_constant<int, ACT_ELU>{}, std::false_type{});
           else if (act == ACT_GELU) stage_rows(std::integral_constant<int, ACT_GELU>{}, std::false_type{});
           else stage_rows(std::integral_constant<int, ACT_NONE>{}, std::false_type{});
+          if (etr) p.trace[4 * 8 + 7] = clock64();
           fence_proxy_async_smem();
+          if (etr) p.trace[5 * 8 + 7] = clock64();
           named_bar_sync(3, NDT);
+          if (etr) p.trace[6 * 8 + 7] = clock64();
           if (dt == 0) {
             const CUtensorMap* tm = second ? &tmC2 : &tmC;
             for (int g8 = 0; g8 < BN / 32; ++g8) {

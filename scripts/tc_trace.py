@@ -11,10 +11,12 @@ if mode == "lin":
     nk = K // 32
 else:  # conv in time-major layout: B Cin Cout k s T pre
     B, Cin, Cout, k, s, T, pre = [int(v) for v in sys.argv[2:9]]
+    use_r = len(sys.argv) > 9 and sys.argv[9] == "1"
     buf = torch.randn(k - s + T, B, Cin, device="cuda"); w = torch.randn(Cout, k * Cin, device="cuda")
     out = torch.empty(T // s, B, Cout, device="cuda")
+    res = torch.randn(T // s, B, Cout, device="cuda") if use_r else None
     plan = ops.TcGemm(buf, 0, Cin, B * Cin, Cin, B, k - s + T, w, Cin, out, 0, Cout, B * Cout, B, T // s, taps=k, tap_do=1, o_mul=s,
-                      pre_act=pre, post_act=pre, precision=prec)
+                      pre_act=0, post_act=pre, precision=prec, R=res, r_i_stride=Cout, r_o_stride=B * Cout)
     nk = k * Cin // 32
 gx, gy, bn = C.c_int32(), C.c_int32(), C.c_int32()
 _lib.lib().rstnet_tc_gemm_grid(plan._h, C.byref(gx), C.byref(gy), C.byref(bn))
@@ -34,8 +36,8 @@ print(f"CTA lifetime ns: mean {life.mean():.0f} min {life.min():.0f} max {life.m
       f"main {(c[:,2]-c[:,1]).float().mean():.0f} ns; all CTAs span {int(c[:,3].max()) - g0} ns")
 order = torch.argsort(c[:, 0])
 print("first CTA starts (ns):", [int(c[i, 0]) - g0 for i in order[:4]], " 149th..:", "")
-print("epilogue stamps (end, pre-bar, post-bar, staged, p0 phase1 done, p0 stored, p1 phase1, p1 stored):", [int(t[k, 7]) - t0 for k in range(8)])
+print("epilogue stamps (end, pre-bar1, post-bar1, boxes free / residual landed, staged, fenced, post-bar3, next tile's drain start):", [int(t[k, 7]) - t0 if int(t[k, 7]) else -1 for k in range(8)])
 print("kit  prod  landed  xformed  mma_start mma_issued | drain_b drain_e")
-for k in range(min(nk, 16)):
+for k in range(min(max(nk, 4), 16)):
     r = [int(v) - t0 if int(v) else -1 for v in t[k]]
     print(f"{k:3d} {r[0]:6d} {r[1]:7d} {r[2]:8d} {r[3]:9d} {r[4]:9d} | {r[5]:7d} {r[6]:7d}")
