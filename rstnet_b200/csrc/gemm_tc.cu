@@ -324,12 +324,11 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   using Cfg = TsCfg<BN>;
   constexpr int S = Cfg::STAGES;
   constexpr int CH = TC_CHUNK_STAGES;
-  static_assert(CH == 4 && TS_NA == 4, "the static chunk schedule assumes 4 stages per chunk and 4 TMEM A stages");
-  // chunk variants: chunk c of this CTA's stream uses smem stages (4c + u) % S, u = 0..3; the pattern repeats every NV
-  // chunks, and because each smem stage is then used an even number of times per period its mbarrier parity depends
-  // only on (variant, u)
-  constexpr int NV = S / (S % 4 == 0 ? 4 : (S % 2 == 0 ? 2 : 1));
-  static_assert(((4 * NV / S) & 1) == 0, "stage parity must be static");
+  static_assert(CH == 4 && TS_NA == 4, "a chunk is at most 4 stages = the 4 TMEM A stages");
+  // Stage g of this CTA's stream (all its tiles back to back, NO padding: a tile contributes exactly taps * kchunks
+  // stages, its last chunk may be short) uses smem slot g % S and TMEM A slot g % 4; parities follow from g.  Round 1
+  // padded every tile to whole 4-stage chunks, which made a K = 32 tile (the 24 kHz 1x1 convs) pay four A loads,
+  // four transforms and 32 MMAs for one stage of work.
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment as pointer arithmetic on the __shared__ array (an integer round trip would demote every later
   // access through `smem` to generic LD / ST)
@@ -351,11 +350,9 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const bool tr = p.trace && blockIdx.x == 0;
   if (timed) p.cta_times[blockIdx.x * 4 + 0] = gtime();
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  // A tile's K loop is padded to whole 4-stage chunks.  A padding stage is an ordinary stage whose weight box lies past
-  // the end of K: TMA zero-fills it, so its MMAs add exactly 0 and no role needs a special case.
+  // A tile's K loop = taps * kchunks stages of 32 elements, in chunks of up to 4 stages (one accumulator promotion each).
   const int total_k = p.taps * p.kchunks;
-  const int kpad = (total_k + CH - 1) / CH * CH;
-  const int nchunks = kpad / CH;
+  const int nchunks = (total_k + CH - 1) / CH;
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int tr_ti = my_tiles > 3 ? 3 : 0;   // the traced tile: steady state when the CTA has several
@@ -380,91 +377,74 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (timed) p.cta_times[blockIdx.x * 4 + 1] = gtime();
 
   if (warp == 0) {
-    // ---- TMA producer: one elected thread runs a whole 4-stage chunk with compile-time stage slots
-    int kc = 0, ci = 0, co = 0, n0 = 0, kit = 0;
-    bool first_tile = true;
-    auto chunk = [&](auto vtag) {
-      constexpr int V = decltype(vtag)::value;
-      if (elect_one()) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int s = (4 * V + u) % S;
-          const uint32_t par = (uint32_t)(((4 * V + u) / S) & 1);
-          mbar_wait(&empty[s], par ^ 1);
-          if (tr && first_tile) p.trace[(kit + u) * 8 + 0] = clock64();
-          uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-          mbar_arrive_expect_tx(&full[s], TC_A_BYTES + 2 * Cfg::B_BYTES);
-          tma_load_3d(st, &tmA, &full[s], kc * TC_BKE, ci, co);
-          tma_load_3d(st + TC_A_BYTES, &tmW3, &full[s], (kit + u) * TC_BKE, n0, 0);   // tap * Kc + kc * 32 == kit * 32
-          if (++kc == p.kchunks) { kc = 0; ci += p.tap_di; co += p.tap_do; }
-        }
-      }
-      __syncwarp();
-    };
-    int v = 0;
+    // ---- TMA producer: one elected thread per chunk
+    int kc = 0, ci = 0, co = 0, n0 = 0;
+    int s = 0;            // smem slot of the next stage (g % S, kept as a running counter: no division on this thread's path)
+    uint32_t sph = 0;     // (g / S) & 1
+    const bool leader = elect_one();   // ONE election: the running counters live in this lane's registers
     for (int ti = 0; ti < my_tiles; ++ti) {
       const int t = blockIdx.x + ti * gridDim.x;
       const int nt = t % p.n_tiles, mt = t / p.n_tiles;
       n0 = nt * BN; ci = (mt % p.i_tiles) * TC_BM; co = (mt / p.i_tiles) * p.o_mul; kc = 0;
-      first_tile = ti == tr_ti;
-      for (kit = 0; kit < kpad; kit += 4) {
-        switch (v) {
-          case 0: chunk(std::integral_constant<int, 0>{}); break;
-          case 1: chunk(std::integral_constant<int, 1 % NV>{}); break;
-          case 2: chunk(std::integral_constant<int, 2 % NV>{}); break;
-          case 3: chunk(std::integral_constant<int, 3 % NV>{}); break;
-          default: chunk(std::integral_constant<int, 4 % NV>{}); break;
+      const bool first_tile = ti == tr_ti;
+      if (leader) {
+        for (int kit = 0; kit < total_k; ++kit) {
+          mbar_wait(&empty[s], sph ^ 1u);
+          if (tr && first_tile) p.trace[kit * 8 + 0] = clock64();
+          uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[s], TC_A_BYTES + 2 * Cfg::B_BYTES);
+          tma_load_3d(st, &tmA, &full[s], kc * TC_BKE, ci, co);
+          tma_load_3d(st + TC_A_BYTES, &tmW3, &full[s], kit * TC_BKE, n0, 0);   // tap * Kc + kc * 32 == kit * 32
+          if (++kc == p.kchunks) { kc = 0; ci += p.tap_di; co += p.tap_do; }
+          if (++s == S) { s = 0; sph ^= 1u; }
         }
-        if (++v == NV) v = 0;
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ---- MMA issue: per k-step  D[hh | hl] (+)= A_hi x [B_hi; B_lo]  (one N = 2*BN MMA), then  D[hl] += A_lo x B_hi
     constexpr uint32_t idesc2 = instr_desc(2u, TC_BM, 2 * BN), idesc1 = instr_desc(2u, TC_BM, BN);
     const uint64_t desc0 = smem_desc_sw128(smem_u32(smem));   // stage s adds s * STAGE_BYTES / 16 to the address field
-    int cc = 0, kit = 0;
-    bool first_tile = true;
-    auto chunk = [&](auto vtag) {
-      constexpr int V = decltype(vtag)::value;
-      if (elect_one()) {
-        const int buf = cc & 1;
-        const uint32_t pa = (uint32_t)(cc & 1);
-        mbar_wait(&acc_empty[buf], (uint32_t)(((cc >> 1) & 1) ^ 1));
-        const uint32_t d0 = tmem_base + (uint32_t)(buf * TC_NACC * BN), d1 = d0 + (uint32_t)BN;
+    int cc = 0;
+    int s = 0;                  // g % S as a running counter
+    uint32_t ga = 0;            // g % 8: TMEM A slot = ga & 3, its phase bit = ga >> 2
+    uint64_t db = desc0 + (uint64_t)(TC_A_BYTES >> 4);   // weight-tile descriptor of smem slot s
+    const bool leader = elect_one();
+    for (int ti = 0; ti < my_tiles; ++ti) {
+      const bool first_tile = ti == tr_ti;
+      if (leader) {
+        for (int kit = 0; kit < total_k; kit += CH, ++cc) {
+          const int nst = total_k - kit < CH ? total_k - kit : CH;
+          const int buf = cc & 1;
+          mbar_wait(&acc_empty[buf], (uint32_t)(((cc >> 1) & 1) ^ 1));
+          const uint32_t d0 = tmem_base + (uint32_t)(buf * TC_NACC * BN), d1 = d0 + (uint32_t)BN;
+          auto stage = [&](int u, bool first, bool last) {
+            const uint32_t sa = ga & 3u;
+            mbar_wait(&a_ready[sa], ga >> 2);   // implies full[s]: the transform waited for it
+            tc_fence_after();
+            if (tr && first_tile) p.trace[(kit + u) * 8 + 3] = clock64();
+            const uint32_t ah = a_tmem0 + sa * 64u, al = ah + 32u;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int s = (4 * V + u) % S;
-          mbar_wait(&a_ready[u], pa);   // implies full[s]: the transform waited for it
-          tc_fence_after();
-          if (tr && first_tile) p.trace[(kit + u) * 8 + 3] = clock64();
-          const uint32_t ah = a_tmem0 + (uint32_t)(u * 64), al = ah + 32u;
-          const uint64_t db = desc0 + (uint64_t)((s * Cfg::STAGE_BYTES + TC_A_BYTES) >> 4);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            mma_tf32_ts(d0, ah + (uint32_t)(8 * k), db + (uint64_t)(2 * k), idesc2, (u == 0 && k == 0) ? 0u : 1u);
-            mma_tf32_ts(d1, al + (uint32_t)(8 * k), db + (uint64_t)(2 * k), idesc1, 1u);
+            for (int k = 0; k < 4; ++k) {
+              mma_tf32_ts(d0, ah + (uint32_t)(8 * k), db + (uint64_t)(2 * k), idesc2, (first && k == 0) ? 0u : 1u);
+              mma_tf32_ts(d1, al + (uint32_t)(8 * k), db + (uint64_t)(2 * k), idesc1, 1u);
+            }
+            tc_commit(&empty[s]);
+            tc_commit(&a_free[sa]);
+            if (last) tc_commit(&acc_full[buf]);
+            if (tr && first_tile) p.trace[(kit + u) * 8 + 4] = clock64();
+            ga = (ga + 1u) & 7u;
+            db += (uint64_t)(Cfg::STAGE_BYTES >> 4);
+            if (++s == S) { s = 0; db = desc0 + (uint64_t)(TC_A_BYTES >> 4); }
+          };
+          if (nst == CH) {
+            stage(0, true, false); stage(1, false, false); stage(2, false, false); stage(3, false, true);
+          } else {
+            for (int u = 0; u < nst; ++u) stage(u, u == 0, u == nst - 1);
           }
-          tc_commit(&empty[s]);
-          tc_commit(&a_free[u]);
-          if (u == 3) tc_commit(&acc_full[buf]);
-          if (tr && first_tile) p.trace[(kit + u) * 8 + 4] = clock64();
         }
       }
       __syncwarp();
-    };
-    int v = 0;
-    for (int ti = 0; ti < my_tiles; ++ti) {
-      first_tile = ti == tr_ti;
-      for (kit = 0; kit < kpad; kit += 4, ++cc) {
-        switch (v) {
-          case 0: chunk(std::integral_constant<int, 0>{}); break;
-          case 1: chunk(std::integral_constant<int, 1 % NV>{}); break;
-          case 2: chunk(std::integral_constant<int, 2 % NV>{}); break;
-          case 3: chunk(std::integral_constant<int, 3 % NV>{}); break;
-          default: chunk(std::integral_constant<int, 4 % NV>{}); break;
-        }
-        if (++v == NV) v = 0;
-      }
     }
   } else if (warp < 10) {
     // transform: two groups of 4 warps alternate stages; thread = one A row (TMEM lane).  It never looks at tile
@@ -474,12 +454,10 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t rowoff = (uint32_t)(row * 128 + ((row & 7) << 4));   // chunk j of the swizzled row: rowoff ^ (j << 4)
     const uint32_t smem0 = smem_u32(smem);
     const uint32_t ta0 = a_tmem0 + ((uint32_t)(q * 32) << 16);
-    const int my_total = my_tiles * kpad;
+    const int my_total = my_tiles * total_k;
     auto run = [&](auto act_tag) {
       constexpr bool ACT = decltype(act_tag)::value;
-      int kit = grp;   // stage index inside the tile (kpad is even, so a group keeps its parity across tiles)
-      for (int g = grp; g < my_total; g += 2, kit += 2) {
-        if (kit >= kpad) kit -= kpad;
+      for (int g = grp; g < my_total; g += 2) {
         const int s = g % S, sa = g % TS_NA;
         // Order matters.  With an odd stage count the previous fill of slot s (stage g - S) belongs to the OTHER transform
         // group, so this thread may get here before that fill has even landed; a parity wait on full[s] would then be
@@ -488,7 +466,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // full[s] is in this stage's phase, so waiting for it second is exact.
         mbar_wait(&a_free[sa], ((g / TS_NA) & 1) ^ 1);
         mbar_wait(&full[s], (g / S) & 1);
-        if (tr && q == 0 && lane == 0 && g >= tr_ti * kpad && g < (tr_ti + 1) * kpad) p.trace[(g - tr_ti * kpad) * 8 + 1] = clock64();
+        if (tr && q == 0 && lane == 0 && g >= tr_ti * total_k && g < (tr_ti + 1) * total_k) p.trace[(g - tr_ti * total_k) * 8 + 1] = clock64();
         tc_fence_after();
         const uint32_t base = smem0 + (uint32_t)(s * Cfg::STAGE_BYTES) + rowoff;
         uint32_t hi[32], lo[32];
@@ -513,7 +491,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&a_ready[sa]);
-        if (tr && q == 0 && lane == 0 && g >= tr_ti * kpad && g < (tr_ti + 1) * kpad) p.trace[(g - tr_ti * kpad) * 8 + 2] = clock64();
+        if (tr && q == 0 && lane == 0 && g >= tr_ti * total_k && g < (tr_ti + 1) * total_k) p.trace[(g - tr_ti * total_k) * 8 + 2] = clock64();
       }
     };
     if (p.pre_act != ACT_NONE) run(std::true_type{}); else run(std::false_type{});

@@ -25,8 +25,10 @@ class Bar:
         return (self.phase & 1) != parity
 
 
-def simulate(S: int, n_stages: int, seed: int, full_first: bool, tma_in_order: bool):
-    """returns None, or a string describing the first protocol violation."""
+def simulate(S: int, n_stages: int, seed: int, full_first: bool, tma_in_order: bool, tile_k: int = 16):
+    """returns None, or a string describing the first protocol violation.  The CTA's stream is n_stages / tile_k tiles of
+    tile_k stages each; a tile is cut in chunks of up to 4 stages (the last one may be short), one accumulator hand-over per
+    chunk -- the unpadded schedule of round 2."""
     rnd = random.Random(seed)
     full, empty = [Bar() for _ in range(S)], [Bar() for _ in range(S)]
     a_ready, a_free = [Bar() for _ in range(NA)], [Bar() for _ in range(NA)]
@@ -40,16 +42,25 @@ def simulate(S: int, n_stages: int, seed: int, full_first: bool, tma_in_order: b
     xf = [{"g": 0, "step": 0}, {"g": 1, "step": 0}]
     mma = {"g": 0, "step": 0}
     drain = {"c": 0}
-    n_chunks = n_stages // CH
-    nv = S // (4 if S % 4 == 0 else (2 if S % 2 == 0 else 1))
+    assert n_stages % tile_k == 0
+    chunk_of, first_of, last_of = [], [], []      # per stage: chunk index in the stream, first / last stage of its chunk?
+    c = 0
+    for t in range(n_stages // tile_k):
+        for k in range(tile_k):
+            chunk_of.append(c)
+            first_of.append(k % CH == 0)
+            last = k % CH == CH - 1 or k == tile_k - 1
+            last_of.append(last)
+            if last:
+                c += 1
+    n_chunks = c
 
     def step_producer():
         g = prod["g"]
         if g >= n_stages:
             return False
-        v, u = (g // CH) % nv, g % CH
-        s = (4 * v + u) % S
-        par = ((4 * v + u) // S) & 1                      # the kernel's compile-time parity
+        s = g % S
+        par = (g // S) & 1
         if not empty[s].passed(par ^ 1):
             return False
         slot[s] = None
@@ -91,17 +102,17 @@ def simulate(S: int, n_stages: int, seed: int, full_first: bool, tma_in_order: b
         g = mma["g"]
         if g >= n_stages:
             return False
-        cc, u = g // CH, g % CH
+        cc, sa = chunk_of[g], g % NA
         buf, s = cc & 1, g % S
         if mma["step"] == 0:
-            if u == 0 and not acc_empty[buf].passed(((cc >> 1) & 1) ^ 1):
+            if first_of[g] and not acc_empty[buf].passed(((cc >> 1) & 1) ^ 1):
                 return False
             mma["step"] = 1
             return True
-        if not a_ready[u].passed(cc & 1):
+        if not a_ready[sa].passed((g // NA) & 1):
             return False
-        if tmem_a[u] != g or slot[s] != g:
-            raise AssertionError(f"MMA of stage {g} saw A stage {tmem_a[u]} / smem slot {slot[s]}")
+        if tmem_a[sa] != g or slot[s] != g:
+            raise AssertionError(f"MMA of stage {g} saw A stage {tmem_a[sa]} / smem slot {slot[s]}")
         mma_q.append(g)
         mma["g"], mma["step"] = g + 1, 0
         return True
@@ -112,9 +123,9 @@ def simulate(S: int, n_stages: int, seed: int, full_first: bool, tma_in_order: b
         g = mma_q.pop(0)
         empty[g % S].arrive()
         a_free[g % NA].arrive()
-        if g % CH == CH - 1:
-            acc[(g // CH) & 1] = g // CH
-            acc_full[(g // CH) & 1].arrive()
+        if last_of[g]:
+            acc[chunk_of[g] & 1] = chunk_of[g]
+            acc_full[chunk_of[g] & 1].arrive()
         return True
 
     def step_drain():
@@ -149,11 +160,14 @@ def simulate(S: int, n_stages: int, seed: int, full_first: bool, tma_in_order: b
 
 
 @pytest.mark.parametrize("S", [5, 6])
-def test_kernel_wait_order_is_safe(S):
-    """the order the kernel uses (a_free, then full): no violation under any schedule tried."""
-    for seed in range(300):
+@pytest.mark.parametrize("tile_k", [1, 2, 5, 6, 16])
+def test_kernel_wait_order_is_safe(S, tile_k):
+    """the order the kernel uses (a_free, then full): no violation under any schedule tried, for short-K tiles (one
+    stage per tile, short last chunks) as well as long ones."""
+    n = 80 // tile_k * tile_k
+    for seed in range(120):
         for in_order in (True, False):
-            assert simulate(S, 80, seed, full_first=False, tma_in_order=in_order) is None, (S, seed, in_order)
+            assert simulate(S, n, seed, full_first=False, tma_in_order=in_order, tile_k=tile_k) is None, (S, tile_k, seed, in_order)
 
 
 def test_model_catches_the_original_wait_order_with_five_stages():
