@@ -303,7 +303,7 @@ template <int BN>
 struct TsCfg {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = TC_A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = BN == 64 ? 5 : 6;
+  static constexpr int STAGES = BN == 64 ? 5 : 8;
   static constexpr int OUT_LD = BN + 4;                       // padded row of the epilogue staging tile (floats)
   static constexpr int BOXSET_BYTES = (BN / 32) * TC_BM * 128;   // [BN/32] swizzled [128 x 32] fp32 boxes of the TMA-store epilogue
   static constexpr int OUT_BYTES = 2 * BOXSET_BYTES;          // two box sets (residual layers alternate per tile); the fallback transpose (4*32*OUT_LD*4) fits inside
@@ -506,9 +506,13 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int t = blockIdx.x + ti * gridDim.x;
       const int nt = t % p.n_tiles, mt = t / p.n_tiles;
       const int i0 = (mt % p.i_tiles) * TC_BM, ot = mt / p.i_tiles, n0 = nt * BN;
-      float* sb = sbs + (ti & 1) * 2 * BN;
-      if (dt < BN) sb[dt] = (p.bias && n0 + dt < p.N) ? p.bias[n0 + dt] : 0.f;
-      else if (dt < 2 * BN) sb[dt] = (p.scale && n0 + dt - BN < p.N) ? p.scale[n0 + dt - BN] : 1.f;
+      // bias | scale of the tile's columns -> smem (double buffered); with a single N tile they are the same for every tile
+      const bool sb_fixed = p.n_tiles == 1;
+      float* sb = sbs + (sb_fixed ? 0 : (ti & 1)) * 2 * BN;
+      if (!sb_fixed || ti == 0) {
+        if (dt < BN) sb[dt] = (p.bias && n0 + dt < p.N) ? p.bias[n0 + dt] : 0.f;
+        else if (dt < 2 * BN) sb[dt] = (p.scale && n0 + dt - BN < p.N) ? p.scale[n0 + dt - BN] : 1.f;
+      }
       // Residual tile -> epilogue boxes by TMA.  Residual layers alternate between two box sets (and two mbarriers): the
       // residual of tile t+1 is requested from the epilogue of tile t, as soon as the store of tile t-1 has been read out of
       // the set it is going to land in, so its latency overlaps the staging and the store of tile t.  (A load landing in
@@ -572,32 +576,55 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           // [BN/32][128 rows][128 B] boxes, 1024-aligned; set 1 = odd tiles of residual layers / the second output of dual-output layers
           // single-output layers alternate the two box sets per tile, dual-output layers per output: either way the set
           // staged next was last read by the store before the most recent one, so ONE store may stay in flight
-          uint8_t* boxes = reinterpret_cast<uint8_t*>(out_stage) + (((p.R || nout == 1) ? (ti & 1) : oi) ? Cfg::BOXSET_BYTES : 0);
+          // Box set k is OWNED by drain thread 32 k (lane 0 of drain warp k): it issues every TMA store that reads the
+          // set, waits for its own stores' read-out before the set is rewritten, and requests the residual tiles that land
+          // in it -- so the two sets' serial duties (store issue ~450 clk, read-out wait + residual request ~1 000 clk) run on
+          // two threads instead of queueing on one.
+          const int set = (p.R || nout == 1) ? (ti & 1) : oi;
+          const bool owner = dt == 32 * set;
+          uint8_t* boxes = reinterpret_cast<uint8_t*>(out_stage) + (set ? Cfg::BOXSET_BYTES : 0);
           if (!p.R) {
-            if (dt == 0) bulk_wait_read1();
+            if (owner) bulk_wait_read0();          // this thread's previous store from the set
             named_bar_sync(2, NDT);
           }
           if (etr) p.trace[3 * 8 + 7] = clock64();
           auto stage_rows = [&](auto act_c, auto res_c) {   // one instantiation per activation: only the executed one is fetched
             constexpr int ACTC = decltype(act_c)::value;
             constexpr bool RES = decltype(res_c)::value;
+            // The operands of column group lc + 4 (bias, scale, residual) are loaded BEFORE the result of group lc is
+            // stored: the compiler cannot tell the box stores from the bias / scale loads (all shared memory) and would
+            // otherwise serialise load -> math -> store per group (255 clk per group, 2 000 clk per 128 x 64 tile).
+            auto slot_of = [&](int lc) {
+              const int c = cbeg + lc;
+              return reinterpret_cast<float4*>(boxes + (c >> 5) * (TC_BM * 128) + rsw + ((((uint32_t)((c & 31) >> 2)) ^ rx) << 4));
+            };
+            float4* slot = slot_of(0);
+            float4 bb = *reinterpret_cast<const float4*>(sb + cbeg), ss = *reinterpret_cast<const float4*>(sb + BN + cbeg);
+            float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (RES) rr = *slot;
 #pragma unroll
             for (int lc = 0; lc < CW; lc += 4) {          // register index static, box / slot from the runtime column
-              const int c = cbeg + lc;
-              uint8_t* bx = boxes + (c >> 5) * (TC_BM * 128) + rsw;
-              const uint32_t j = (uint32_t)((c & 31) >> 2);
-              const float4 bb = *reinterpret_cast<const float4*>(sb + c);
-              const float4 ss = *reinterpret_cast<const float4*>(sb + BN + c);
+              float4* slot_n = slot;
+              float4 bbn = bb, ssn = ss, rrn = rr;
+              if (lc + 4 < CW) {
+                slot_n = slot_of(lc + 4);
+                bbn = *reinterpret_cast<const float4*>(sb + cbeg + lc + 4);
+                ssn = *reinterpret_cast<const float4*>(sb + BN + cbeg + lc + 4);
+                if (RES) rrn = *slot_n;
+              }
               float4 v = make_float4((acc[lc] + bb.x) * ss.x, (acc[lc + 1] + bb.y) * ss.y, (acc[lc + 2] + bb.z) * ss.z, (acc[lc + 3] + bb.w) * ss.w);
-              float4* slot = reinterpret_cast<float4*>(bx + ((j ^ rx) << 4));
-              if (RES) { const float4 rr = *slot; v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
+              if (RES) { v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
               *slot = apply_act4_tc<ACTC>(v);
+              slot = slot_n; bb = bbn; ss = ssn; rr = rrn;
             }
           };
           if (p.R) {
             mbar_wait(&r_full[ti & 1], (uint32_t)((ti >> 1) & 1));   // one residual load per tile
-            if (dt == 0 && ti + 1 < my_tiles) {
-              bulk_wait_read0();        // the store of tile ti-1 (issued a whole residual latency ago) has left the other set
+            // The next tile's residual is requested NOW, before this tile is staged: its latency under load is ~3 000 clk
+            // (the residual is the block input, long evicted from L2); requesting it after the store cost 68 -> 81 us on
+            // the 24 kHz 1x1 conv.
+            if (dt == 32 * ((ti + 1) & 1) && ti + 1 < my_tiles) {   // owner of the OTHER set
+              bulk_wait_read0();        // its store of tile ti-1 has left that set
               request_residual(ti + 1);
             }
             if (etr) p.trace[3 * 8 + 7] = clock64();
@@ -611,7 +638,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (etr) p.trace[5 * 8 + 7] = clock64();
           named_bar_sync(3, NDT);
           if (etr) p.trace[6 * 8 + 7] = clock64();
-          if (dt == 0) {
+          if (owner) {
             const CUtensorMap* tm = second ? &tmC2 : &tmC;
             for (int g8 = 0; g8 < BN / 32; ++g8) {
               const int n = n0 + g8 * 32;
@@ -695,7 +722,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }  // DW == 4
     }
   }
-  if (threadIdx.x == 320) bulk_wait0();   // the issuing thread's TMA stores are complete before the CTA (and its smem) goes away
+  if (threadIdx.x == 320 || threadIdx.x == 352) bulk_wait0();   // the issuing threads' TMA stores are complete before the CTA (and its smem) goes away
   if (timed) p.cta_times[blockIdx.x * 4 + 2] = gtime();
   tc_fence_before();
   __syncthreads();
