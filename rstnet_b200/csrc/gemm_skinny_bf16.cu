@@ -33,7 +33,134 @@ struct SkParams {
   int M, N, K, MB;           // MB = M rounded up to 16 (UMMA N)
   int splits, k_iters;       // k_iters = 64-element chunks per split
   int force_partial;         // write fp32 partials even with one split (a fused finalize kernel consumes them)
+  // ---- in-kernel finalize ("tail"): once the `splits` CTAs of an N tile have all arrived on tail_cnt[tile], each of them
+  // sums the partials (in split order) of its share of the rows and applies the epilogue: no finalize kernel is launched
+  int tail;                  // 0 off; 1 plain (+R) -> out; 2 (+R) -> out, RMSNorm(out) * norm_w -> aux; 3 SiLU gating -> aux
+  int* tail_cnt;             // [n_tiles] arrivals per tile (per tile pair for SiLU) | [n_tiles] "seen" | done | passed; self-resetting
+  float* tail_ssq;           // [n_tiles][M] per-tile sums of squares of the stored bf16 row pieces (mode 2)
+  const __nv_bfloat16* norm_w;
+  __nv_bfloat16* aux;
+  float eps;
+  int kyutai;
 };
+
+// In-kernel finalize of one N tile, shared by the CTAs that computed its K slices: once all of them have arrived, CTA
+// `part` of `nparts` finalizes rows part, part + nparts, ... with its 128 epilogue threads (t = 0..127).  A warp takes one
+// row at a time: 32 lanes x 4 columns = the tile's 128 columns, so a row's sum of squares is one warp reduction; RB rows
+// and all splits are loaded before the first add (one L2 latency per batch, not per row).  Arithmetic as the stand-alone
+// finalize kernels below (partials added in split order, bf16 roundings in the same places).
+constexpr int SK_RB = 4;
+__device__ __forceinline__ void skinny_tail(const SkParams& p, int tile, int part, int nparts, int t) {
+  const int n_tiles = (int)gridDim.x;
+  const long long MN = (long long)p.M * p.N;
+  const int lane = t & 31, w = t >> 5;
+  const int I = p.N / 2;
+  const int n = tile * SK_BN + 4 * lane;
+  const bool nv = p.tail == 3 ? n < I : n < p.N;
+  auto row_of = [&](int j) { return part + nparts * (w + 4 * j); };
+  for (int j0 = 0; row_of(j0) < p.M; j0 += SK_RB) {
+    float4 v[SK_RB], u[SK_RB];
+#pragma unroll
+    for (int r = 0; r < SK_RB; ++r) v[r] = u[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nv) {
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        if (s < p.splits) {
+#pragma unroll
+          for (int r = 0; r < SK_RB; ++r) {
+            const int m = row_of(j0 + r);
+            if (m < p.M) {
+              const float* src = p.partial + (long long)s * MN + (long long)m * p.N + n;
+              const float4 a = __ldcg(reinterpret_cast<const float4*>(src));
+              v[r].x += a.x; v[r].y += a.y; v[r].z += a.z; v[r].w += a.w;
+              if (p.tail == 3) {
+                const float4 b = __ldcg(reinterpret_cast<const float4*>(src + I));
+                u[r].x += b.x; u[r].y += b.y; u[r].z += b.z; u[r].w += b.w;
+              }
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < SK_RB; ++r) {
+      const int m = row_of(j0 + r);
+      if (m >= p.M) break;
+      if (p.tail == 3) {
+        if (nv) {
+          auto gate = [](float av, float bv) {
+            av = __bfloat162float(__float2bfloat16(av));
+            bv = __bfloat162float(__float2bfloat16(bv));
+            const float sl = __bfloat162float(__float2bfloat16(av / (1.0f + expf(-av))));
+            return sl * bv;
+          };
+          __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(p.aux + (long long)m * I + n);
+          o2[0] = __floats2bfloat162_rn(gate(v[r].x, u[r].x), gate(v[r].y, u[r].y));
+          o2[1] = __floats2bfloat162_rn(gate(v[r].z, u[r].z), gate(v[r].w, u[r].w));
+        }
+        continue;
+      }
+      float ss = 0.f;
+      if (nv) {
+        const long long i = (long long)m * p.N + n;
+        float4 x = v[r];
+        if (p.R) {
+          const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(p.R + i);
+          const float2 a = __bfloat1622float2(r2[0]), b = __bfloat1622float2(r2[1]);
+          x.x += a.x; x.y += a.y; x.z += b.x; x.w += b.y;
+        }
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(p.out + i);
+        o2[0] = lo; o2[1] = hi;
+        const float2 fa = __bfloat1622float2(lo), fb = __bfloat1622float2(hi);  // the norm sees the stored bf16 values
+        ss = fmaf(fa.x, fa.x, ss); ss = fmaf(fa.y, fa.y, ss); ss = fmaf(fb.x, fb.x, ss); ss = fmaf(fb.y, fb.y, ss);
+      }
+      if (p.tail == 2) {
+        ss = warp_sum(ss);
+        if (lane == 0) p.tail_ssq[(long long)tile * p.M + m] = ss;
+      }
+    }
+  }
+  if (p.tail != 2) return;
+  // ---- RMSNorm needs whole rows: publish this CTA's sums, wait for every CTA of the grid (all co-resident: the plan
+  // takes this path only when n_tiles * splits <= 2 CTAs x SMs)
+  const int n_ctas = n_tiles * (int)gridDim.y;
+  int* done = p.tail_cnt + 2 * n_tiles;
+  int* passed = done + 1;
+  __threadfence();
+  named_bar_sync(1, 128);
+  if (t == 0) {
+    atomicAdd(done, 1);
+    while (*reinterpret_cast<volatile int*>(done) < n_ctas) __nanosleep(32);
+    __threadfence();
+  }
+  named_bar_sync(1, 128);
+  for (int j = 0; row_of(j) < p.M; ++j) {
+    const int m = row_of(j);
+    float tot = 0.f;
+    for (int tt = lane; tt < n_tiles; tt += 32) tot += __ldcg(p.tail_ssq + (long long)tt * p.M + m);
+    tot = warp_sum(tot);
+    const float mean = tot / (float)p.N;
+    const float r = p.kyutai ? rsqrtf(p.eps + mean) : rsqrtf(mean + p.eps);
+    if (nv) {
+      const long long i = (long long)m * p.N + n;
+      const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(p.out + i);
+      const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(p.norm_w + n);
+      const float2 xa = __bfloat1622float2(x2[0]), xb = __bfloat1622float2(x2[1]);
+      const float2 wa = __bfloat1622float2(w2[0]), wb = __bfloat1622float2(w2[1]);
+      float4 o;
+      if (p.kyutai) { o.x = xa.x * (wa.x * r); o.y = xa.y * (wa.y * r); o.z = xb.x * (wb.x * r); o.w = xb.y * (wb.y * r); }
+      else          { o.x = (xa.x * r) * wa.x; o.y = (xa.y * r) * wa.y; o.z = (xb.x * r) * wb.x; o.w = (xb.y * r) * wb.y; }
+      __nv_bfloat162* a2 = reinterpret_cast<__nv_bfloat162*>(p.aux + i);
+      a2[0] = __floats2bfloat162_rn(o.x, o.y);
+      a2[1] = __floats2bfloat162_rn(o.z, o.w);
+    }
+  }
+  if (t == 0) {
+    // every CTA has seen done == n_ctas before it counts itself here: the last one re-arms both counters
+    if (atomicAdd(passed, 1) == n_ctas - 1) { *done = 0; *passed = 0; }
+  }
+}
 
 template <int STAGES>
 __global__ void __launch_bounds__(SK_THREADS, 2)
@@ -132,6 +259,27 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
           }
         }
       }
+    }
+    if (p.tail) {
+      const int t = threadIdx.x - 64;
+      const int n_tiles = (int)gridDim.x, half = n_tiles / 2;
+      const bool gate = p.tail == 3;             // SiLU: the a and b tiles of a column block are finalized together
+      const int cnt = gate ? (int)blockIdx.x % half : (int)blockIdx.x;
+      const int nparts = gate ? 2 * p.splits : p.splits;
+      const int part = gate ? 2 * (int)blockIdx.y + ((int)blockIdx.x >= half ? 1 : 0) : (int)blockIdx.y;
+      int* arrive = p.tail_cnt + cnt;
+      int* seen = p.tail_cnt + n_tiles + cnt;
+      __threadfence();                 // this CTA's partials are visible before its arrival is counted
+      named_bar_sync(1, 128);
+      if (t == 0) {
+        atomicAdd(arrive, 1);
+        while (*reinterpret_cast<volatile int*>(arrive) < nparts) __nanosleep(32);
+        // the last CTA to have seen the full count re-arms the pair of counters for the next launch
+        if (atomicAdd(seen, 1) == nparts - 1) { *arrive = 0; *seen = 0; }
+        __threadfence();
+      }
+      named_bar_sync(1, 128);
+      skinny_tail(p, cnt, part, nparts, t);
     }
   }
   tc_fence_before();
@@ -277,6 +425,7 @@ struct rstnet_skinny_plan {
   __nv_bfloat16* aux;
   float eps;
   int kyutai;
+  void* tail_mem;   // counters + per-tile sums of the in-kernel finalize (owned)
 };
 
 extern "C" int rstnet_skinny_gemm_create_fused(const void* X, const void* W, const void* R, void* out, float* partial_ws,
@@ -359,6 +508,44 @@ extern "C" int rstnet_skinny_gemm_create_fused(const void* X, const void* W, con
   // 4 stages (<= 98 KB with M <= 64): two CTAs fit per SM, so a GEMM whose tile count is not a multiple of 148
   // still keeps every SM streaming (bandwidth-bound CTAs progress at equal rates) and prologues overlap main loops
   pl->smem = (size_t)4 * stage_bytes + 1024 + 256;
+  // In-kernel finalize instead of a second launch: possible whenever fp32 partials are written, the grid is co-resident
+  // (every CTA waits for the other K slices of its tile, the RMSNorm tail for the whole grid) and, for SiLU, the a / b
+  // column blocks are whole tiles.  OPT-IN (RSTNET_SKINNY_TAIL=1), parity-tested, because it does not pay: the tail is a
+  // chain of ~6-8 dependent L2 round trips (release fence, arrival atomic, poll, partial loads, sums-of-squares exchange,
+  // stores) = 5-8 us, as much as the launch boundary it removes.  Measured on the 7B frame at B = 64: temporal part
+  // 14.47 ms with the tail vs 14.48 ms with 96 finalize launches; depth part (192 small GEMMs) 4.5 ms vs 3.0 ms.
+  p.tail = 0; p.tail_cnt = nullptr; p.tail_ssq = nullptr; pl->tail_mem = nullptr;
+  p.norm_w = pl->norm_w; p.aux = pl->aux; p.eps = eps; p.kyutai = kyutai;
+  {
+    static const bool tail_on = []() { const char* e = getenv("RSTNET_SKINNY_TAIL"); return e && e[0] == '1'; }();
+    const bool partials = splits > 1 || p.force_partial;
+    // every CTA waits for the other K slices of its tile (and, for RMSNorm, for the whole grid): the grid must be co-resident
+    int sms = 148, dev = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static unsigned long long attr = 0;
+    smem_optin(gemm_skinny_kernel<4>, 200 * 1024, attr);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gemm_skinny_kernel<4>, SK_THREADS, pl->smem) != cudaSuccess) {
+      cudaGetLastError();
+      per_sm = 0;
+    }
+    const bool resident = (long long)n_tiles * splits <= (long long)per_sm * sms;
+    const bool silu_ok = fin_mode != 2 || ((N / 2) % SK_BN == 0 && n_tiles % 2 == 0);
+    if (tail_on && partials && partial_ws && N % 4 == 0 && silu_ok && resident && splits <= 8) {
+      const size_t cnt_bytes = ((size_t)(2 * n_tiles + 2) * sizeof(int) + 15) & ~(size_t)15;
+      const size_t bytes = cnt_bytes + (size_t)n_tiles * M * sizeof(float);
+      if (cudaMalloc(&pl->tail_mem, bytes) != cudaSuccess || cudaMemset(pl->tail_mem, 0, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        if (pl->tail_mem) cudaFree(pl->tail_mem);
+        delete pl;
+        set_error("skinny_gemm_create: could not allocate the finalize counters (%zu bytes)", bytes);
+        return 3;
+      }
+      p.tail = fin_mode == 1 ? 2 : (fin_mode == 2 ? 3 : 1);
+      p.tail_cnt = (int*)pl->tail_mem;
+      p.tail_ssq = (float*)((char*)pl->tail_mem + cnt_bytes);
+    }
+  }
   *outp = pl;
   return 0;
 }
@@ -371,6 +558,7 @@ extern "C" int rstnet_skinny_gemm_run(const rstnet_skinny_plan* pl, rstnet_strea
   launch_pdl(gemm_skinny_kernel<4>, pl->grid, dim3(SK_THREADS), pl->smem, st, pl->tmW, pl->tmX, pl->p);
   count_launch();
   if (int e = check_launch("gemm_skinny")) return e;
+  if (pl->p.tail) return 0;          // finalized inside the kernel
   const long long MN = (long long)pl->p.M * pl->p.N;
   if (pl->fin_mode == 1) {
     launch_pdl(skinny_finalize_norm_kernel, dim3(pl->p.M * FIN_CL), dim3(256), 0, st, (const float*)pl->p.partial, pl->p.R, pl->p.out, pl->norm_w,
@@ -395,7 +583,10 @@ extern "C" int rstnet_skinny_gemm_run(const rstnet_skinny_plan* pl, rstnet_strea
   return 0;
 }
 
-extern "C" void rstnet_skinny_gemm_destroy(rstnet_skinny_plan* pl) { delete pl; }
+extern "C" void rstnet_skinny_gemm_destroy(rstnet_skinny_plan* pl) {
+  if (pl && pl->tail_mem) cudaFree(pl->tail_mem);
+  delete pl;
+}
 extern "C" int64_t rstnet_skinny_gemm_workspace(int32_t M, int32_t N, int32_t max_splits) {
   return (int64_t)max_splits * M * N * (int64_t)sizeof(float);
 }

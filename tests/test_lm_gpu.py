@@ -702,3 +702,18 @@ def test_depth_frame_kernel_vs_multi_launch_path(small_lm):
     ref = torch.stack(ref, 1)
     assert _cos(new[0], ref) >= 0.999 and _rel(new[0], ref) <= 5e-2, (_cos(new[0], ref), _rel(new[0], ref))
     m.check_device_errors()
+
+
+def test_in_kernel_finalize_tail_opt_in():
+    """RSTNET_SKINNY_TAIL=1 (read once per process): split-K partials are reduced, normalised / gated inside the GEMM
+    kernel by the CTAs of each tile instead of by a finalize launch.  Same arithmetic, so the GEMM, whole-frame and 7B-width
+    tests must pass unchanged in a child process with the switch on."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, RSTNET_SKINNY_TAIL="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+                        "-k", "skinny_gemm_vs_torch or forward_step_matches_stepwise_api or cfg3_shape_wrapped_ring"],
+                       env=env, capture_output=True, text=True, timeout=900, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
+    assert " passed" in r.stdout
