@@ -464,6 +464,19 @@ def lm_decode_bench(dev, steps: int, warmup: int):
         e1.record()
         torch.cuda.synchronize()
         ms_e2e = e0.elapsed_time(e1) / steps
+        # in-graph split of the step: the temporal transformer's own graph, replayed alone (position rewound each time
+        # so it keeps attending the full window); the rest of the frame graph is the depth transformer + sampling
+        n_t = max(3, steps)
+        for i in range(n_t + 2):
+            if i == 2:
+                torch.cuda.synchronize()
+                e0.record()
+            st._replay(("temporal",), st._temporal)
+            st.offset.fill_(KV + 8)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_temporal = e0.elapsed_time(e1) / n_t
+        st.pos_host[:] = KV + 8
         # per-kernel roofline pass: one eager frame with events around every GEMM / attention launch
         m.use_cuda_graphs = False
         m.forward_step(seq)
@@ -491,6 +504,18 @@ def lm_decode_bench(dev, steps: int, warmup: int):
            "roofline": {"bound": "hbm", "achieved": step_bytes / 1e9 / (ms * 1e-3), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": step_bytes / 1e9 / (ms * 1e-3) / peaks["hbm_gbs"], "peak_source": peaks["source"]},
            "attention_kernel": agg(rec["attn"]), "gemm_kernels": agg(rec["gemm"])}
+    att_ms = out["attention_kernel"]["ms"]
+    tw = 2.0 * (cfg.n_layer * (3 * cfg.n_embd * cfg.n_embd + cfg.n_embd * cfg.n_embd + 3 * cfg.n_embd * cfg.intermediate_size)
+                + cfg.padded_vocab_size * cfg.n_embd)      # qkv + proj + (fc_1, fc_2, down) per layer + the text head, bf16
+    rest = ms_temporal - att_ms
+    out["in_graph_split_ms"] = {
+        "temporal_graph": ms_temporal, "attention_32_layers": att_ms, "temporal_gemms_and_small_kernels": rest,
+        "depth_transformer_and_sampling": ms - ms_temporal, "temporal_weight_gbytes": tw / 1e9,
+        "temporal_gemm_in_graph_gbs": tw / 1e9 / (rest * 1e-3) if rest > 0 else None,
+        "temporal_gemm_in_graph_frac": tw / 1e9 / (rest * 1e-3) / peaks["hbm_gbs"] if rest > 0 else None,
+        "note": "temporal_graph = the temporal transformer's CUDA graph replayed alone; the eager per-launch GEMM times above include "
+                "event / launch overhead and understate the in-graph rate; the in-graph figure charges the GEMMs with every "
+                "finalize / RoPE / embedding launch of the temporal part"}
     shapes = {}
     for it in rec["gemm"]:
         d = shapes.setdefault(str(it[3]), [0, 0.0, 0.0])

@@ -232,7 +232,9 @@ int rstnet_skinny_gemm_create(const void* X, const void* W, const void* R, void*
 /* Same GEMM with a fused finalize: fin_mode 1: out = bf16(acc + R) AND aux_out = RMSNorm(out) * norm_w (the pre-norm of
  * the following GEMM: Block.forward's `x = attn + x; norm_2(x)`, llama_streaming.py:834-853; kyutai != 0 selects
  * modules/transformer.py:34-48); fin_mode 2: aux_out[m][c] = silu(acc[m][c]) * acc[m][N/2 + c] (LLaMAMLP / ActivationGating),
- * `out` unused.  Both need partial_ws. */
+ * `out` unused.  Both need partial_ws.  fin_mode 3: the same gating for a weight whose rows are INTERLEAVED (row 2c = the
+ * gate row c, row 2c + 1 = the value row c): aux_out[m][c] = silu(acc[m][2c]) * acc[m][2c + 1] computed in the GEMM's own
+ * epilogue (one K slice, no workspace, no finalize launch); N even. */
 int rstnet_skinny_gemm_create_fused(const void* X, const void* W, const void* R, void* out, float* partial_ws,
                                     int32_t M, int32_t N, int32_t K, int32_t max_splits, int32_t fin_mode,
                                     const void* norm_w, void* aux_out, float eps, int32_t kyutai,

@@ -35,7 +35,8 @@ struct SkParams {
   int force_partial;         // write fp32 partials even with one split (a fused finalize kernel consumes them)
   // ---- in-kernel finalize ("tail"): once the `splits` CTAs of an N tile have all arrived on tail_cnt[tile], each of them
   // sums the partials (in split order) of its share of the rows and applies the epilogue: no finalize kernel is launched
-  int tail;                  // 0 off; 1 plain (+R) -> out; 2 (+R) -> out, RMSNorm(out) * norm_w -> aux; 3 SiLU gating -> aux
+  int tail;                  // 0 off; 1 plain (+R) -> out; 2 (+R) -> out, RMSNorm(out) * norm_w -> aux; 3 SiLU gating -> aux;
+                             // 4: SiLU gating in the epilogue itself (one split, weight rows interleaved a_0 b_0 a_1 b_1 ...)
   int* tail_cnt;             // [n_tiles] arrivals per tile (per tile pair for SiLU) | [n_tiles] "seen" | done | passed; self-resetting
   float* tail_ssq;           // [n_tiles][M] per-tile sums of squares of the stored bf16 row pieces (mode 2)
   const __nv_bfloat16* norm_w;
@@ -244,6 +245,23 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       tmem_ld_wait();
+      if (p.tail == 4) {
+        // rows 2j / 2j+1 of the interleaved weight are a_j / b_j: neighbouring lanes hold the gate and the value of
+        // output column j, so SiLU gating needs one shuffle and no fp32 partials (gating.py:12-21; lit_model.py:399-403)
+        const int I = p.N / 2;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float v = __uint_as_float(r[j]);
+          const float o = __shfl_xor_sync(0xffffffffu, v, 1);
+          const int m = c0 + j;
+          if (!(lane & 1) && nv && m < p.M) {
+            const float a = __bfloat162float(__float2bfloat16(v)), b = __bfloat162float(__float2bfloat16(o));
+            const float sl = __bfloat162float(__float2bfloat16(a / (1.0f + expf(-a))));
+            p.aux[(long long)m * I + (n >> 1)] = __float2bfloat16(sl * b);
+          }
+        }
+        continue;
+      }
       if (nv) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -260,7 +278,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constan
         }
       }
     }
-    if (p.tail) {
+    if (p.tail && p.tail != 4) {
       const int t = threadIdx.x - 64;
       const int n_tiles = (int)gridDim.x, half = n_tiles / 2;
       const bool gate = p.tail == 3;             // SiLU: the a and b tiles of a column block are finalized together
@@ -442,10 +460,15 @@ extern "C" int rstnet_skinny_gemm_create_fused(const void* X, const void* W, con
                                                int32_t M, int32_t N, int32_t K, int32_t max_splits, int32_t fin_mode,
                                                const void* norm_w, void* aux_out, float eps, int32_t kyutai,
                                                rstnet_skinny_plan** outp) {
-  RSTNET_REQUIRE(X && W && outp && (out || fin_mode == 2), "skinny_gemm_create: null pointer");
-  RSTNET_REQUIRE(fin_mode >= 0 && fin_mode <= 2, "skinny_gemm_create: bad fin_mode");
+  RSTNET_REQUIRE(X && W && outp && (out || fin_mode >= 2), "skinny_gemm_create: null pointer");
+  RSTNET_REQUIRE(fin_mode >= 0 && fin_mode <= 3, "skinny_gemm_create: bad fin_mode");
+  if (fin_mode == 3) {   // SiLU gating on interleaved weight rows, finished in the GEMM epilogue: one K slice, no workspace
+    RSTNET_REQUIRE(aux_out && N % 2 == 0, "skinny_gemm_create: interleaved SiLU gating needs an aux output and an even N (N=%d)", N);
+    partial_ws = nullptr;
+    max_splits = 1;
+  }
   RSTNET_REQUIRE(fin_mode != 1 || N % (4 * FIN_CL) == 0, "skinny_gemm_create: fused RMSNorm needs N %% 16 == 0 (N=%d)", N);
-  RSTNET_REQUIRE(fin_mode == 0 || (partial_ws && aux_out && N % 4 == 0 && (fin_mode == 2 || norm_w)),
+  RSTNET_REQUIRE(fin_mode == 0 || fin_mode == 3 || (partial_ws && aux_out && N % 4 == 0 && (fin_mode == 2 || norm_w)),
                  "skinny_gemm_create: fused finalize needs a workspace, an aux output and N %% 4 == 0");
   RSTNET_REQUIRE(M >= 1 && M <= 128 && N >= 1 && K >= SK_BK && K % SK_BK == 0, "skinny_gemm_create: need 1<=M<=128, K %% 64 == 0 (M=%d N=%d K=%d)", M, N, K);
   RSTNET_REQUIRE((uintptr_t)X % 16 == 0 && (uintptr_t)W % 16 == 0, "skinny_gemm_create: X and W must be 16-byte aligned");
@@ -501,7 +524,7 @@ extern "C" int rstnet_skinny_gemm_create_fused(const void* X, const void* W, con
   p.M = M; p.N = N; p.K = K; p.MB = MB; p.splits = splits;
   pl->fin_mode = fin_mode; pl->norm_w = (const __nv_bfloat16*)norm_w; pl->aux = (__nv_bfloat16*)aux_out; pl->eps = eps; pl->kyutai = kyutai;
   // a fused finalize always reads fp32 partials, so the main kernel takes the split path even with one split
-  p.force_partial = fin_mode != 0;
+  p.force_partial = fin_mode == 1 || fin_mode == 2;
   p.k_iters = ceil_div(kchunks, splits);
   pl->grid = dim3((unsigned)n_tiles, (unsigned)splits);
   const int stage_bytes = SK_W_BYTES + ((MB * 128 + 1023) & ~1023);
@@ -546,6 +569,7 @@ extern "C" int rstnet_skinny_gemm_create_fused(const void* X, const void* W, con
       p.tail_ssq = (float*)((char*)pl->tail_mem + cnt_bytes);
     }
   }
+  if (fin_mode == 3) p.tail = 4;
   *outp = pl;
   return 0;
 }

@@ -21,6 +21,7 @@ dtype recipe of `GPT(config).to(device, bfloat16)` (infer_no_streaming.py:104-10
 from __future__ import annotations
 
 import ctypes as C
+import os
 from contextlib import contextmanager
 from dataclasses import dataclass
 from typing import Dict, Optional
@@ -89,22 +90,36 @@ class Config:
         return (21 * d) // 8 if ff == 4 * d else (2 * ff) // 3
 
 
+# A/B switch (tuning aid): RSTNET_LM_GATE_INTERLEAVE=0 packs fc_1 | fc_2 stacked and gates in a finalize kernel
+_GATE_INTERLEAVE = os.environ.get("RSTNET_LM_GATE_INTERLEAVE", "1") != "0"
+
+
+def interleave_gate_rows(w_gate: torch.Tensor, w_value: torch.Tensor) -> torch.Tensor:
+    """[gate row 0, value row 0, gate row 1, value row 1, ...]: the packing the GEMM's in-epilogue SiLU gating expects (the
+    two rows of an output column sit in neighbouring lanes of the tcgen05 epilogue; fc_1 / fc_2 of LLaMAMLP,
+    lit_model.py:399-403, or the halves of ActivationGating.linear_in, modules/gating.py:12-21)."""
+    return torch.stack([w_gate, w_value], dim=1).reshape(2 * w_gate.shape[0], w_gate.shape[1]).contiguous()
+
+
 class SkinnyGemm:
     """rstnet_skinny_gemm_* plan: out[m,n] = sum_k X[m,k] W[n,k] (+ R[m,n]), bf16, optionally with a fused finalize:
-    norm_w/aux -> aux = RMSNorm(out) * norm_w (the next GEMM's pre-norm); silu_out -> silu_out = silu(a) * b."""
+    norm_w/aux -> aux = RMSNorm(out) * norm_w (the next GEMM's pre-norm); silu_out -> silu_out = silu(a) * b, with
+    [a; b] = the two halves of the result or, `interleaved` (see `interleave_gate_rows`), its even / odd columns -- the latter
+    is finished in the GEMM's epilogue without a finalize launch."""
 
     def __init__(self, X: torch.Tensor, W: torch.Tensor, out: Optional[torch.Tensor], R: Optional[torch.Tensor],
                  ws: Optional[torch.Tensor], max_splits: int = 8, norm_w: Optional[torch.Tensor] = None,
-                 aux: Optional[torch.Tensor] = None, eps: float = 0.0, kyutai: bool = False, silu_out: Optional[torch.Tensor] = None):
+                 aux: Optional[torch.Tensor] = None, eps: float = 0.0, kyutai: bool = False, silu_out: Optional[torch.Tensor] = None,
+                 interleaved: bool = False):
         M, K = X.shape
         N = W.shape[0]
         assert W.shape[1] == K and X.dtype == W.dtype == torch.bfloat16 and X.is_contiguous() and W.is_contiguous()
         if N % 4 != 0:
             ws = None  # split-K / fused finalize work on 4-element groups
-        mode = 2 if silu_out is not None else (1 if norm_w is not None else 0)
-        if mode and ws is None:
+        mode = (3 if interleaved else 2) if silu_out is not None else (1 if norm_w is not None else 0)
+        if mode in (1, 2) and ws is None:
             raise RstnetError("fused finalize needs a workspace and N % 4 == 0")
-        aux_t = silu_out if mode == 2 else aux
+        aux_t = silu_out if mode >= 2 else aux
         self._keep = (X, W, out, R, ws, norm_w, aux_t)
         self._h = C.c_void_p()
         self.flops = 2.0 * M * N * K
@@ -544,20 +559,24 @@ class _LMState:
 
         if m._packed is None:
             pk = self._pack_temporal(P)
-            if Hp != H or self.frame_kernel:
-                for l in range(c.codecformer_layers):
-                    for k in range(c.dep_q):
-                        w_in = P[m._DN["dlayer"].format(l) + f".gating.{k}.linear_in.weight"]
-                        w_out = P[m._DN["dlayer"].format(l) + f".gating.{k}.linear_out.weight"]
-                        gi = z(2 * Hp, D)
-                        gi[:H], gi[Hp:Hp + H] = w_in[:H], w_in[H:]
-                        if self.frame_kernel:
-                            # rows interleaved in 8-row groups [a_8u..8u+7 ; b_8u..8u+7]: one mma row block then holds a
-                            # gate / value pair per thread and SiLU gating happens in the GEMM's epilogue
-                            gi = torch.stack([gi[:Hp].view(Hp // 8, 8, D), gi[Hp:].view(Hp // 8, 8, D)], 1).reshape(2 * Hp, D).contiguous()
+            # depth gating weights: K padded to the GEMM granularity.  They keep the stacked [gate; value] form + finalize
+            # kernel: with 44 column tiles the GEMM wants two K slices (13.4 us vs 14.5 us for one, scripts/skinny_sweep.py),
+            # which the in-epilogue gating cannot have -- measured 3.3 ms vs 3.0 ms for the depth part of a frame.
+            for l in range(c.codecformer_layers if (Hp != H or self.frame_kernel) else 0):
+                for k in range(c.dep_q):
+                    w_in = P[m._DN["dlayer"].format(l) + f".gating.{k}.linear_in.weight"]
+                    w_out = P[m._DN["dlayer"].format(l) + f".gating.{k}.linear_out.weight"]
+                    gi = z(2 * Hp, D)
+                    gi[:H], gi[Hp:Hp + H] = w_in[:H], w_in[H:]
+                    if self.frame_kernel:
+                        # rows interleaved in 8-row groups [a_8u..8u+7 ; b_8u..8u+7]: one mma row block then holds a
+                        # gate / value pair per thread and SiLU gating happens in the GEMM's epilogue
+                        gi = torch.stack([gi[:Hp].view(Hp // 8, 8, D), gi[Hp:].view(Hp // 8, 8, D)], 1).reshape(2 * Hp, D).contiguous()
+                    go = w_out
+                    if Hp != H:
                         go = z(D, Hp)
                         go[:, :H] = w_out
-                        pk[f"gin.{l}.{k}"], pk[f"gout.{l}.{k}"] = gi, (go if Hp != H else w_out)
+                    pk[f"gin.{l}.{k}"], pk[f"gout.{l}.{k}"] = gi, go
             pk["frame_kernel"] = self.frame_kernel
             m._packed = pk
         elif m._packed.get("frame_kernel") != self.frame_kernel:
@@ -617,8 +636,11 @@ class _LMState:
     def _pack_temporal(self, P):
         """one-time repacked weights of the temporal transformer (fc_1 | fc_2 as one GEMM)"""
         c = self.c
-        return {f"fc12.{l}": torch.cat([P[f"transformer.h.{l}.mlp.fc_1.linear.weight"],
-                                        P[f"transformer.h.{l}.mlp.fc_2.linear.weight"]], 0).contiguous()
+        if not _GATE_INTERLEAVE:
+            return {f"fc12.{l}": torch.cat([P[f"transformer.h.{l}.mlp.fc_1.linear.weight"],
+                                            P[f"transformer.h.{l}.mlp.fc_2.linear.weight"]], 0).contiguous() for l in range(c.n_layer)}
+        return {f"fc12.{l}": interleave_gate_rows(P[f"transformer.h.{l}.mlp.fc_1.linear.weight"],
+                                                  P[f"transformer.h.{l}.mlp.fc_2.linear.weight"])
                 for l in range(c.n_layer)}
 
     def _build_temporal(self, P, G, z, parent):
@@ -672,7 +694,7 @@ class _LMState:
                 # x = attn + x ; xn = norm_2(x)   (Block.forward, llama_streaming.py:846-849) in the GEMM's finalize
                 proj=G(self.att, P[f"{p}.attn.proj.linear.weight"], self.x, self.x, norm_w=n2[l], aux=self.xn, eps=c.norm_eps),
                 # hmid = silu(fc_1 x) * fc_2 x   (LLaMAMLP, lit_model.py:399-403)
-                fc=G(self.xn, m._packed[f"fc12.{l}"], None, silu_out=self.hmid),
+                fc=G(self.xn, m._packed[f"fc12.{l}"], None, silu_out=self.hmid, interleaved=_GATE_INTERLEAVE),
                 # x = mlp + x ; xn = norm_1 of the next block (or ln_f -> transformer_out)
                 down=G(self.hmid, P[f"{p}.mlp.proj.linear.weight"], self.x, self.x, norm_w=self.ln_f if last else n1[l + 1],
                        aux=self.out if last else self.xn, eps=c.norm_eps)))

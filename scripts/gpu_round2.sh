@@ -20,5 +20,9 @@ fi
 if [ "$STAGE" = "all" ] || [ "$STAGE" = "sanitizer" ]; then
   timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gemm_tc_gpu.py -x -q 2>&1 | grep -v "Host Frame" | head -60 > gpurun_out/r2_sanitizer_memcheck.log
   timeout 600 compute-sanitizer --tool racecheck --print-limit 20 python -m pytest tests/test_gemm_tc_gpu.py -x -q -k "ts or persistent or conv" 2>&1 | tail -25 > gpurun_out/r2_sanitizer_racecheck.log
+  # LM kernels changed in round 2: cp.async-ring attention (incl. the key-split form), skinny GEMM epilogues / in-kernel finalize
+  timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_lm_gpu.py -x -q -k "attention or skinny_gemm or norms" 2>&1 | grep -v "Host Frame" | tail -30 > gpurun_out/r2_sanitizer_memcheck_lm.log
+  RSTNET_SKINNY_TAIL=1 timeout 600 compute-sanitizer --tool racecheck --print-limit 20 python -m pytest tests/test_lm_gpu.py -x -q -k "attention or skinny_gemm" 2>&1 | tail -25 > gpurun_out/r2_sanitizer_racecheck_lm.log
   tail -n 4 gpurun_out/r2_sanitizer_memcheck.log; tail -n 4 gpurun_out/r2_sanitizer_racecheck.log
+  tail -n 4 gpurun_out/r2_sanitizer_memcheck_lm.log; tail -n 4 gpurun_out/r2_sanitizer_racecheck_lm.log
 fi

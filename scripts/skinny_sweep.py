@@ -1,5 +1,5 @@
 """Tuning aid: time the LM weight-streaming GEMM (+ its finalize) for each split-K factor, per layer shape.
-Each (shape, splits) runs over 16 distinct weight matrices back to back (working set >> L2) behind a spin kernel."""
+Each (shape, splits) runs over 16..64 distinct weight matrices back to back (working set >> L2) as one replayed CUDA graph."""
 import os, sys, torch
 sys.path.insert(0, ".")
 from rstnet_b200.lm import SkinnyGemm
@@ -36,17 +36,23 @@ for name in only:
         for p in plans[:2]:
             p.run()
         torch.cuda.synchronize()
-        best = 1e9
-        for _ in range(3):
-            torch.cuda._sleep(4_000_000)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+        # timed as a replayed CUDA graph (how the decode step runs them): kernel + finalize launch boundaries included
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
             for p in plans:
                 p.run()
+        g.replay()
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
             e1.record()
             torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1) * 1e3 / reps)
         res[s] = round(best, 1)
+        del g
         del plans
     os.environ.pop("RSTNET_SKINNY_SPLITS", None)
     print(name, (N, K), mode, res, flush=True)
