@@ -22,7 +22,9 @@ if [ "$STAGE" = "all" ] || [ "$STAGE" = "sanitizer" ]; then
   timeout 600 compute-sanitizer --tool racecheck --print-limit 20 python -m pytest tests/test_gemm_tc_gpu.py -x -q -k "ts or persistent or conv" 2>&1 | tail -25 > gpurun_out/r2_sanitizer_racecheck.log
   # LM kernels changed in round 2: cp.async-ring attention (incl. the key-split form), skinny GEMM epilogues / in-kernel finalize
   timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_lm_gpu.py -x -q -k "attention or skinny_gemm or norms" 2>&1 | grep -v "Host Frame" | tail -30 > gpurun_out/r2_sanitizer_memcheck_lm.log
-  RSTNET_SKINNY_TAIL=1 timeout 600 compute-sanitizer --tool racecheck --print-limit 20 python -m pytest tests/test_lm_gpu.py -x -q -k "attention or skinny_gemm" 2>&1 | tail -25 > gpurun_out/r2_sanitizer_racecheck_lm.log
+  # (the tests' torch SDPA reference kernel, fmha_cutlassF, reports hazards of its own: count ours separately)
+  timeout 600 compute-sanitizer --tool racecheck --print-limit 20 python -m pytest tests/test_lm_gpu.py -x -q -k "rope_append_and_ring or skinny_gemm" > gpurun_out/_race_lm_full.log 2>&1
+  { echo "hazard lines naming rstnet:: kernels: $(grep -c 'rstnet::' gpurun_out/_race_lm_full.log)"; echo "hazard lines naming torch's fmha_cutlassF reference kernel: $(grep -c 'fmha_cutlassF' gpurun_out/_race_lm_full.log)"; tail -n 3 gpurun_out/_race_lm_full.log; } > gpurun_out/r2_sanitizer_racecheck_lm.log; rm -f gpurun_out/_race_lm_full.log
   tail -n 4 gpurun_out/r2_sanitizer_memcheck.log; tail -n 4 gpurun_out/r2_sanitizer_racecheck.log
   tail -n 4 gpurun_out/r2_sanitizer_memcheck_lm.log; tail -n 4 gpurun_out/r2_sanitizer_racecheck_lm.log
 fi
