@@ -535,7 +535,16 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
       };
-      if (p.tma_store && p.R && dt == 0 && ti == 0) request_residual(0);
+      if (p.tma_store && p.R) {
+        if (dt == 0 && ti == 0) request_residual(0);
+        // The NEXT tile's residual is requested at the top of this tile, by the owner of the other box set, as soon as its
+        // store of tile ti-1 has been read out: the residual is the block input, long evicted from L2, and takes ~3 000 clk
+        // under load -- most of a tile period.  (Requested after this tile's store instead: 68 -> 81 us on the 24 kHz 1x1 conv.)
+        if (dt == 32 * ((ti + 1) & 1) && ti + 1 < my_tiles) {
+          bulk_wait_read0();
+          request_residual(ti + 1);
+        }
+      }
       float acc[CW];
 #pragma unroll
       for (int j = 0; j < CW; ++j) acc[j] = 0.f;
@@ -620,13 +629,6 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           };
           if (p.R) {
             mbar_wait(&r_full[ti & 1], (uint32_t)((ti >> 1) & 1));   // one residual load per tile
-            // The next tile's residual is requested NOW, before this tile is staged: its latency under load is ~3 000 clk
-            // (the residual is the block input, long evicted from L2); requesting it after the store cost 68 -> 81 us on
-            // the 24 kHz 1x1 conv.
-            if (dt == 32 * ((ti + 1) & 1) && ti + 1 < my_tiles) {   // owner of the OTHER set
-              bulk_wait_read0();        // its store of tile ti-1 has left that set
-              request_residual(ti + 1);
-            }
             if (etr) p.trace[3 * 8 + 7] = clock64();
             if (act == ACT_ELU) stage_rows(std::integral_constant<int, ACT_ELU>{}, std::true_type{});
             else stage_rows(std::integral_constant<int, ACT_NONE>{}, std::true_type{});
