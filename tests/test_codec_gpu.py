@@ -300,6 +300,11 @@ def test_streaming_vs_reference_golden_and_batch(golden_dir, codec, graphs, tc):
     g = np.load(os.path.join(golden_dir, "mimi_stream6.npz"))
     x = S.synthetic_audio(2, 1920 * 6, seed=int(g["audio_seed"])).to(DEV)
     codec.use_cuda_graphs, codec.streaming_tensor_cores = graphs, tc
+    # float64 top-1/top-2 decision margins of this fixture (oracle: StreamingCodec.encode + rvq_margins(last_latent).min over
+    # the 8 levels): all >= 1.9e-4 except stream 0, frame 4 (4.7e-6) -- the only frame whose indices may legitimately flip
+    # under fp32 reordering (margin < 1e-4)
+    near_tie = torch.zeros(2, 6, dtype=torch.bool)
+    near_tie[0, 4] = True
     wtol = (2e-3 if codec.decoder_precision == 1 else 1e-4) if tc else 1e-4   # single-pass TF32 decoder: stated tolerance
     cs, ws = [], []
     with codec.streaming(2):
@@ -317,13 +322,13 @@ def test_streaming_vs_reference_golden_and_batch(golden_dir, codec, graphs, tc):
         assert torch.equal(codes, b_codes)
         assert _maxdiff(wav, b_wav) == 0.0
     else:
-        assert (codes != b_codes).any(dim=1).float().mean().item() <= 0.1
+        assert not bool(((codes != b_codes).any(dim=1).cpu() & ~near_tie).any())
         assert _maxdiff(wav, b_wav) <= wtol * peak
     d = _maxdiff(wav, torch.from_numpy(g["wav"]))
     bad = (codes.cpu() != torch.from_numpy(g["codes"])).any(dim=1)
     print(f"tc={tc} graphs={graphs}: wav max|d| vs reference {d:.2e}; frames with index mismatch {int(bad.sum())}/12")
     assert d <= wtol * peak
-    assert bad.float().mean().item() <= 0.1
+    assert not bool((bad & ~near_tie).any()), f"index mismatch on a well-separated frame: {bad.nonzero().tolist()}"
     if tc and graphs:   # opt-in single-pass TF32 decoder: stated tolerance 2e-3 of peak
         codec.decoder_precision = 1
         try:
