@@ -193,6 +193,13 @@ int rstnet_ring_attention_f32(const float* qkv, int64_t q_batch_stride, int64_t 
                               int64_t o_batch_stride, int64_t o_time_stride, int32_t batch, int32_t T,
                               int32_t H, int32_t D, int32_t cap, int32_t context, int32_t linear,
                               rstnet_stream_t stream);
+/* Both steps in one launch for a streaming step of T = 2 tokens at D = 64 (the 25 Hz codec transformers): the warp
+ * that owns (stream, head) rotates q in registers, rotates / appends k, v itself and then attends (ring semantics, same
+ * arithmetic as the two calls above; qkv is left untouched). */
+int rstnet_rope_ring_attention_f32(const float* qkv, int64_t q_batch_stride, int64_t q_time_stride, float* kv,
+                                   const int64_t* offset, int32_t offset_stride, const float* freqs, float* out,
+                                   int64_t o_batch_stride, int64_t o_time_stride, int32_t batch, int32_t T, int32_t H,
+                                   int32_t D, int32_t cap, int32_t context, rstnet_stream_t stream);
 
 /* ---- SplitResidualVectorQuantizer.encode (quantization/vq.py:305-315; core_vq.py:179-185,
  * 365-376): x [N, ldx] holds the two projected latents (rvq_first at column 0, rvq_rest at

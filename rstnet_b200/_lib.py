@@ -19,7 +19,7 @@ SYMBOLS = [
     "rstnet_gemm_rows_f32", "rstnet_tc_gemm_create", "rstnet_tc_gemm_run", "rstnet_tc_gemm_destroy", "rstnet_tc_gemm_set_trace", "rstnet_tc_gemm_grid", "rstnet_tf32_split_f32", "rstnet_conv1d_cin1_f32", "rstnet_conv1d_cout1_f32",
     "rstnet_convtr1d_depthwise_f32", "rstnet_rows_fill_f32", "rstnet_rows_copy_table_f32",
     "rstnet_counter_add", "rstnet_layer_norm_f32", "rstnet_rope_kv_append_f32",
-    "rstnet_ring_attention_f32", "rstnet_rvq_encode_workspace", "rstnet_rvq_encode_f32",
+    "rstnet_ring_attention_f32", "rstnet_rope_ring_attention_f32", "rstnet_rvq_encode_workspace", "rstnet_rvq_encode_f32",
     "rstnet_rvq_decode_gather_f32",
     "rstnet_skinny_gemm_workspace", "rstnet_skinny_gemm_create", "rstnet_skinny_gemm_create_fused", "rstnet_skinny_gemm_run", "rstnet_skinny_gemm_destroy",
     "rstnet_lm_embed_sum_bf16", "rstnet_lm_embed_rows_bf16", "rstnet_lm_rms_norm_bf16", "rstnet_lm_rope_kv_append_bf16",
@@ -114,6 +114,7 @@ def lib() -> C.CDLL:
     L.rstnet_layer_norm_f32.argtypes = [vp, i64, vp, vp, vp, i32, i32, i32, f32, vp]
     L.rstnet_rope_kv_append_f32.argtypes = [vp, i64, i64, vp, vp, i32, vp, i32, i32, i32, i32, i32, vp]
     L.rstnet_ring_attention_f32.argtypes = [vp, i64, i64, vp, vp, i32, vp, i64, i64, i32, i32, i32, i32, i32, i32, i32, vp]
+    L.rstnet_rope_ring_attention_f32.argtypes = [vp, i64, i64, vp, vp, i32, vp, vp, i64, i64, i32, i32, i32, i32, i32, i32, vp]
     L.rstnet_rvq_encode_workspace.argtypes = [i64, i32, i32, i32]
     L.rstnet_rvq_encode_workspace.restype = i64
     L.rstnet_rvq_encode_f32.argtypes = [vp, i64, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, i32, vp]

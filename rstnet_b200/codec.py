@@ -179,6 +179,7 @@ class MimiCodec(nn.Module):
         # non-streaming encode / decode of a batch (offline tokenization): batches of at least this many
         # clips run the tcgen05 path (a 128-row tile = 128 clips at one time step), smaller ones the fp32 CUDA-core path
         self.batch_tensor_cores_min = 96
+        self.fused_rope_attention = True     # streaming steps: RoPE + KV append inside the attention launch
 
     # ------------------------------------------------------------------ parameters
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
@@ -665,8 +666,14 @@ class _Plan:
             kvl = kv[l]
             self.add(lambda w=w: ops.layer_norm(X.t, xv[0], x_bs, w["n1w"], w["n1b"], ln, ln_args[0], ln_args[1], D, 1e-5))
             self.linear(ln, self.flat_view(F, D), D, w["in_w"], qkv, self.flat_view(F, 3 * D), 3 * D)
-            self.add(lambda kvl=kvl: ops.rope_kv_append(qkv, q_bs, q_ts, kvl, offset, eng.freqs, B, F, H, hd, cap))
-            self.add(lambda kvl=kvl: ops.ring_attention(qkv, q_bs, q_ts, kvl, offset, att, o_bs, o_ts, B, F, H, hd, cap, m.context, linear))
+            if self.streaming and F == 2 and hd == 64 and m.fused_rope_attention and min(q_bs, q_ts, o_bs, o_ts) % 4 == 0:
+                # one launch: the warp that owns (stream, head) rotates / appends its new k, v and attends
+                self.add(lambda kvl=kvl: ops.rope_ring_attention(qkv, q_bs, q_ts, kvl, offset, eng.freqs, att, o_bs, o_ts, B, F, H, hd,
+                                                                 cap, m.context))
+            else:
+                self.add(lambda kvl=kvl: ops.rope_kv_append(qkv, q_bs, q_ts, kvl, offset, eng.freqs, B, F, H, hd, cap))
+                self.add(lambda kvl=kvl: ops.ring_attention(qkv, q_bs, q_ts, kvl, offset, att, o_bs, o_ts, B, F, H, hd, cap, m.context,
+                                                            linear))
             self.linear(att, self.flat_view(F, D), D, w["out_w"], X.t, xv, D, scale=w["ls1"], R_view=xv)
             self.add(lambda w=w: ops.layer_norm(X.t, xv[0], x_bs, w["n2w"], w["n2b"], ln, ln_args[0], ln_args[1], D, 1e-5))
             self.linear(ln, self.flat_view(F, D), D, w["w1"], ff, self.flat_view(F, FF), FF, post=ACT_GELU)

@@ -226,11 +226,16 @@ __global__ void ring_attention_pair_kernel(const float* __restrict__ qkv, long l
 // 128-bit loads (two rows per instruction), the two half-warps accumulate alternate keys and are added at the end.
 // Ring slots advance incrementally (no per-key modulo).  At a 200-token context this kernel is 16 x 136 us of a
 // 256-stream frame in the one-row-per-lane form (launch list profiles/r1_codec_late_frame_launches_rowperlane_attn.csv).
+// ROPE: the streaming step (T == 2: one warp owns both new tokens of its (stream, head)) rotates q in registers, rotates and
+// appends k, copies v into the ring itself -- arithmetic of rope_kv_append_kernel above -- and then attends; the separate
+// RoPE / append launch (16 per frame) disappears.  The ring is then read with plain loads (the warp reads rows it wrote).
+template <bool ROPE>
 __global__ void __launch_bounds__(128, 4) ring_attention_pair64_kernel(const float* __restrict__ qkv, long long qbs, long long qts,
-                                             const float* __restrict__ kv, const long long* __restrict__ offset, int ostride,
+                                             float* kv, const long long* __restrict__ offset, int ostride,
                                              float* __restrict__ out, long long obs, long long ots, int B, int T, int H,
-                                             int cap, int context, int linear) {
+                                             int cap, int context, int linear, const float* __restrict__ freqs) {
   constexpr int D = 64;
+  auto ldk = [](const float4* p) { return ROPE ? *p : __ldg(p); };
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int P = (T + 1) / 2;
   const long long wid = (long long)blockIdx.x * (blockDim.x / 32) + warp;
@@ -253,6 +258,39 @@ __global__ void __launch_bounds__(128, 4) ring_attention_pair64_kernel(const flo
   const long long off = offset[(long long)b * ostride];
   const long long end = off + T;
   const long long pos0 = off + t0, pos1 = has1 ? pos0 + 1 : pos0;
+  if (ROPE) {
+    // ts = offset.float() + arange(T) in fp32 (rope.py:39); separate mul / sub / add as the eager reference evaluates them
+    auto rotate8 = [&](float* x, float ts) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float ang = __fmul_rn(freqs[4 * sub + i], ts);
+        const float c = cosf(ang), s = sinf(ang);
+        const float xr = x[2 * i], xi = x[2 * i + 1];
+        x[2 * i] = __fsub_rn(__fmul_rn(xr, c), __fmul_rn(xi, s));
+        x[2 * i + 1] = __fadd_rn(__fmul_rn(xr, s), __fmul_rn(xi, c));
+      }
+    };
+    rotate8(qa, __fadd_rn((float)off, (float)t0));
+    if (has1) rotate8(qb, __fadd_rn((float)off, (float)(t0 + 1)));
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) qb[i] = qa[i];
+    }
+    // lanes 0-7 / 8-15: k of token t0 / t0+1 (rotated), lanes 16-23 / 24-31: v of token t0 / t0+1
+    const int tok = grp & 1, is_v = grp >> 1;
+    if (tok == 0 || has1) {
+      const int HD = H * D;
+      const float* src = qkv + b * qbs + (long long)(t0 + tok) * qts + h * D + (is_v ? 2 * HD : HD) + 8 * sub;
+      const float4 s0 = *reinterpret_cast<const float4*>(src), s1 = *reinterpret_cast<const float4*>(src + 4);
+      float x[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+      if (!is_v) rotate8(x, __fadd_rn((float)off, (float)(t0 + tok)));
+      const int slot = (int)((pos0 + tok) % cap);
+      float* dst = kv + (is_v ? (long long)B * H * cap * D : 0) + (((long long)b * H + h) * cap + slot) * D + 8 * sub;
+      *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(x[4], x[5], x[6], x[7]);
+    }
+    __syncwarp();
+  }
   long long lo0 = pos0 - context + 1, lo1 = pos1 - context + 1;
   if (lo0 < 0) lo0 = 0;
   if (lo1 < 0) lo1 = 0;
@@ -282,8 +320,8 @@ __global__ void __launch_bounds__(128, 4) ring_attention_pair64_kernel(const flo
         slot = small_ring ? slot % cap : (slot >= cap ? slot - cap : slot);
         const bool in = p0 + 4 * it + grp <= pos1;
         const float* kr = Kb + (long long)(in ? slot : slot_last) * D + 8 * sub;
-        kq[it][0] = __ldg(reinterpret_cast<const float4*>(kr));
-        kq[it][1] = __ldg(reinterpret_cast<const float4*>(kr + 4));
+        kq[it][0] = ldk(reinterpret_cast<const float4*>(kr));
+        kq[it][1] = ldk(reinterpret_cast<const float4*>(kr + 4));
       }
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
@@ -328,7 +366,7 @@ __global__ void __launch_bounds__(128, 4) ring_attention_pair64_kernel(const flo
       const int j = 2 * i + half;
       int slot = base + j;
       slot = small_ring ? slot % cap : (slot >= cap ? slot - cap : slot);
-      vq[i] = __ldg(reinterpret_cast<const float4*>(Vb + (long long)(j < nk ? slot : slot_last) * D + 4 * vl));
+      vq[i] = ldk(reinterpret_cast<const float4*>(Vb + (long long)(j < nk ? slot : slot_last) * D + 4 * vl));
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -369,6 +407,25 @@ extern "C" int rstnet_rope_kv_append_f32(float* qkv, int64_t q_batch_stride, int
   return check_launch("rope_kv_append");
 }
 
+extern "C" int rstnet_rope_ring_attention_f32(const float* qkv, int64_t q_batch_stride, int64_t q_time_stride, float* kv,
+                                              const int64_t* offset, int32_t offset_stride, const float* freqs, float* out,
+                                              int64_t o_batch_stride, int64_t o_time_stride, int32_t batch, int32_t T, int32_t H,
+                                              int32_t D, int32_t cap, int32_t context, rstnet_stream_t stream) {
+  RSTNET_REQUIRE(qkv && kv && offset && freqs && out, "rope_ring_attention: null pointer");
+  RSTNET_REQUIRE(batch > 0 && H > 0 && cap > 0 && context > 0, "rope_ring_attention: bad shape");
+  RSTNET_REQUIRE(T == 2 && D == 64 && T <= cap, "rope_ring_attention: the fused form covers streaming steps of 2 tokens at head size 64 (T=%d D=%d)", T, D);
+  RSTNET_REQUIRE(((uintptr_t)qkv % 16) == 0 && ((uintptr_t)kv % 16) == 0 && ((uintptr_t)out % 16) == 0 && q_batch_stride % 4 == 0 &&
+                     q_time_stride % 4 == 0 && o_batch_stride % 4 == 0 && o_time_stride % 4 == 0,
+                 "rope_ring_attention: buffers and strides must be 16-byte aligned");
+  const int warps = 4;
+  const long long total = (long long)batch * H;
+  ring_attention_pair64_kernel<true><<<ceil_div(total, warps), warps * 32, 0, (cudaStream_t)stream>>>(
+      qkv, q_batch_stride, q_time_stride, kv, (const long long*)offset, offset_stride ? 1 : 0, out, o_batch_stride, o_time_stride, batch, T, H,
+      cap, context, 0, freqs);
+  count_launch();
+  return check_launch("rope_ring_attention");
+}
+
 extern "C" int rstnet_ring_attention_f32(const float* qkv, int64_t q_batch_stride, int64_t q_time_stride, const float* kv,
                                          const int64_t* offset, int32_t offset_stride, float* out, int64_t o_batch_stride,
                                          int64_t o_time_stride, int32_t batch, int32_t T, int32_t H, int32_t D, int32_t cap,
@@ -382,9 +439,9 @@ extern "C" int rstnet_ring_attention_f32(const float* qkv, int64_t q_batch_strid
                          q_time_stride % 4 == 0 && o_batch_stride % 4 == 0 && o_time_stride % 4 == 0;
   if (T >= 2 && D == 64 && aligned16) {
     const long long total = (long long)batch * ((T + 1) / 2) * H;
-    ring_attention_pair64_kernel<<<ceil_div(total, warps), warps * 32, 0, (cudaStream_t)stream>>>(
-        qkv, q_batch_stride, q_time_stride, kv, (const long long*)offset, ostride, out, o_batch_stride, o_time_stride, batch, T, H, cap,
-        context, linear);
+    ring_attention_pair64_kernel<false><<<ceil_div(total, warps), warps * 32, 0, (cudaStream_t)stream>>>(
+        qkv, q_batch_stride, q_time_stride, const_cast<float*>(kv), (const long long*)offset, ostride, out, o_batch_stride, o_time_stride,
+        batch, T, H, cap, context, linear, nullptr);
   } else if (T >= 2) {
     const long long total = (long long)batch * ((T + 1) / 2) * H;
     ring_attention_pair_kernel<<<ceil_div(total, warps), warps * 32, warps * 2 * D * sizeof(float), (cudaStream_t)stream>>>(

@@ -181,6 +181,14 @@ def rope_kv_append(qkv, q_bs, q_ts, kv, offset, freqs, batch, T, H, D, cap):
                                                     freqs.data_ptr(), batch, T, H, D, cap, _stream()), "rope_kv_append")
 
 
+def rope_ring_attention(qkv, q_bs, q_ts, kv, offset, freqs, out, o_bs, o_ts, batch, T, H, D, cap, context):
+    """rope_kv_append + ring_attention in one launch (streaming steps of 2 tokens, head size 64)."""
+    _cuda(qkv, kv, offset, freqs, out)
+    _lib.check(_lib.lib().rstnet_rope_ring_attention_f32(qkv.data_ptr(), q_bs, q_ts, kv.data_ptr(), offset.data_ptr(), _ostride(offset),
+                                                         freqs.data_ptr(), out.data_ptr(), o_bs, o_ts, batch, T, H, D, cap, context,
+                                                         _stream()), "rope_ring_attention")
+
+
 def ring_attention(qkv, q_bs, q_ts, kv, offset, out, o_bs, o_ts, batch, T, H, D, cap, context, linear):
     _cuda(qkv, kv, offset, out)
     _lib.check(_lib.lib().rstnet_ring_attention_f32(qkv.data_ptr(), q_bs, q_ts, kv.data_ptr(), offset.data_ptr(), _ostride(offset),

@@ -187,6 +187,33 @@ def test_rope_ring_attention_vs_oracle(T, steps, cap, context):
     assert int(offset.item()) == off
 
 
+@pytest.mark.parametrize("T,steps,cap,context,per_stream", [(2, 140, 250, 250, False), (2, 40, 16, 16, True), (2, 30, 33, 20, True)])
+def test_fused_rope_attention_equals_two_launch_form(T, steps, cap, context, per_stream):
+    """rstnet_rope_ring_attention_f32 (RoPE + KV append inside the attention launch, streaming steps of 2 tokens) is
+    bit-identical to rope_kv_append + ring_attention: output rows and ring contents, across ring wrap, with per-stream
+    position counters at different values."""
+    import math
+    B, H, D = 3, 8, 64
+    g = torch.Generator().manual_seed(T * 1000 + steps)
+    ds = torch.arange(D // 2, dtype=torch.float32)
+    freqs = torch.exp(ds * (-math.log(10000.0) * 2 / D)).to(DEV)
+    kv_a = torch.zeros(2, B, H, cap, D, device=DEV)
+    kv_b = torch.zeros(2, B, H, cap, D, device=DEV)
+    start = torch.tensor([0, 5, 3 * cap + 1], dtype=torch.int64) if per_stream else torch.zeros(1, dtype=torch.int64)
+    off_a, off_b = start.clone().to(DEV), start.clone().to(DEV)
+    for step in range(steps):
+        qkv = torch.randn(B, T, 3 * H * D, generator=g).to(DEV)
+        qa, out_a = qkv.clone(), torch.empty(B, T, H * D, device=DEV)
+        out_b = torch.empty(B, T, H * D, device=DEV)
+        ops.rope_kv_append(qa, T * 3 * H * D, 3 * H * D, kv_a, off_a, freqs, B, T, H, D, cap)
+        ops.ring_attention(qa, T * 3 * H * D, 3 * H * D, kv_a, off_a, out_a, T * H * D, H * D, B, T, H, D, cap, context, False)
+        ops.rope_ring_attention(qkv, T * 3 * H * D, 3 * H * D, kv_b, off_b, freqs, out_b, T * H * D, H * D, B, T, H, D, cap, context)
+        ops.counter_add(off_a, T)
+        ops.counter_add(off_b, T)
+        assert torch.equal(out_a, out_b), step
+    assert torch.equal(kv_a, kv_b)
+
+
 def _run_rvq(lat_btd, w, cfg=S.OFFICIAL):
     """lat [B,T,512] on device -> codes via proj GEMM + rvq kernels, using oracle-side packing."""
     B, T, D = lat_btd.shape

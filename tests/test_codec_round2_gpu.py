@@ -268,3 +268,24 @@ def test_offline_tokenization_and_batch_tensor_core_path(official_weights, codec
     assert offline.reconstruct_directory(codec, src, dst) == 1
     rec, sr = offline.read_wav(os.path.join(dst, "a.wav"))
     assert sr == 24000 and rec.numel() == 9600
+
+
+def test_fused_rope_attention_streaming_equals_separate_launches(official_weights):
+    """MimiCodec.fused_rope_attention (default on) only removes 16 launches per frame: codes and PCM of a streaming run
+    are bit-identical with the knob off."""
+    x = S.synthetic_audio(4, 1920 * 5, seed=77).to(DEV)
+    res = []
+    for fused in (True, False):
+        m = MimiCodec(encoder_rates=[8, 6, 5, 4], codebook_size=2048, codebook_dim=256, rvq_layers=8)
+        m.load_state_dict(official_weights, strict=True)
+        m = m.to(DEV).eval()
+        m.fused_rope_attention = fused
+        cs, ws = [], []
+        with m.streaming(4):
+            for i in range(5):
+                c = m.encode(x[..., i * 1920:(i + 1) * 1920])
+                cs.append(c)
+                ws.append(m.decode(c))
+        res.append((torch.cat(cs, -1), torch.cat(ws, -1)))
+    assert torch.equal(res[0][0], res[1][0])
+    assert torch.equal(res[0][1], res[1][1])
