@@ -180,6 +180,9 @@ class MimiCodec(nn.Module):
         # clips run the tcgen05 path (a 128-row tile = 128 clips at one time step), smaller ones the fp32 CUDA-core path
         self.batch_tensor_cores_min = 96
         self.fused_rope_attention = True     # streaming steps: RoPE + KV append inside the attention launch
+        # resblocks up to this width read the raw tensor and apply ELU in the operand transform (_Plan.elu_in_transform).
+        # 0 = never (default): measured 3.16 / 3.20 ms per 256-stream frame step at 128 / 64 vs 3.11 ms with the ELU'd copy
+        self.elu_in_transform_max_channels = 0
 
     # ------------------------------------------------------------------ parameters
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
@@ -548,6 +551,15 @@ class _Plan:
     def buf(self, ctx, T, extra, C) -> _Buf:
         return _Buf(self.B, ctx, T, extra, C, self.eng.device, self.tc)
 
+    def elu_in_transform(self, C: int) -> bool:
+        """Tensor-core plans: does the resblock conv of a C-channel level apply its input ELU in the GEMM's operand transform
+        (reading the raw tensor) instead of reading an ELU'd copy written by the producer?  Same values either way (one
+        ELU implementation, bit-identical results).  The idea: at the wide, shallow levels (24 kHz C = 64, 6 kHz C = 128)
+        the copy is a second 126 / 63 MB tensor per 256-stream frame.  Measured (scripts/codec_ab.py, same box): it does NOT
+        pay -- the 32 extra ex2 per thread and stage on the transform warps cost more than the saved stores (3.16 vs 3.11 ms
+        per frame step), so MimiCodec.elu_in_transform_max_channels defaults to 0."""
+        return self.tc and C <= self.eng.m.elu_in_transform_max_channels and self.precision == 0 and self.eng.m.resblock_tensor_cores
+
     @staticmethod
     def tc_weights(pack):
         """TF32 (hi, lo) split of a weight pack, computed once and cached on the pack."""
@@ -722,8 +734,9 @@ class _EncPlan(_Plan):
         y, ya, h, r_ = [], [], [], []  # ya: ELU'd copies feeding the resblocks' first conv (tensor-core plans)
         C = nf
         for i, ratio in enumerate(eng.enc_ratios):
-            y.append(self.buf(0 if self.tc else m.residual_kernel_size - 1, T[i], 0, C))
-            ya.append(self.buf(m.residual_kernel_size - 1, T[i], 0, C) if self.tc else y[-1])
+            own_copy = self.tc and not self.elu_in_transform(C)
+            y.append(self.buf(0 if own_copy else m.residual_kernel_size - 1, T[i], 0, C))
+            ya.append(self.buf(m.residual_kernel_size - 1, T[i], 0, C) if own_copy else y[-1])
             h.append(self.buf(0, T[i], 0, C // m.compress))
             r_.append(self.buf(ratio, T[i], T[i + 1] * ratio - T[i], C))
             C *= 2
@@ -737,7 +750,7 @@ class _EncPlan(_Plan):
         self._keep = (xproj, work)
 
         # conv0: 1 -> nf, k7 (HBM-bound, CUDA cores)
-        if self.tc:
+        if self.tc and ya[0] is not y[0]:
             self.add(lambda: ops.conv1d_cin1(xin.t, xin.bs, xin.ts, eng.e_conv0_w, eng.e_conv0_b, y[0].t, 0, y[0].bs, y[0].ts, B, L,
                                              nf, k0, ACT_NONE, out2=ya[0].t, out2_off=ya[0].off(ya[0].ctx), act2=ACT_ELU))
         else:
@@ -746,12 +759,12 @@ class _EncPlan(_Plan):
         for i, ratio in enumerate(eng.enc_ratios):
             w1, w2 = eng.e_res[i]
             # SEANetResnetBlock: ELU -> k3 -> ELU -> k1, + skip; the ELU that follows is fused as post_act
-            self.conv(ya[i], 0, 1, w1, h[i], 0, T[i], pre=ACT_NONE if self.tc else ACT_ELU, post=ACT_ELU, ffma=self.tc)
+            self.conv(ya[i], 0, 1, w1, h[i], 0, T[i], pre=ACT_ELU if ya[i] is y[i] else ACT_NONE, post=ACT_ELU, ffma=self.tc)
             self.conv(h[i], 0, 1, w2, r_[i], r_[i].ctx, T[i], post=ACT_ELU, R=y[i], r_row0=y[i].ctx, ffma=self.tc)
             if i + 1 < len(y):
                 nxt = y[i + 1]
                 self.conv(r_[i], 0, ratio, eng.e_down[i], nxt, nxt.ctx, T[i + 1],
-                          out2=ya[i + 1] if self.tc else None, out2_row0=ya[i + 1].ctx)
+                          out2=ya[i + 1] if ya[i + 1] is not nxt else None, out2_row0=ya[i + 1].ctx)
             else:
                 self.conv(r_[i], 0, ratio, eng.e_down[i], y4, y4.ctx, T[i + 1], post=ACT_ELU)
         self.conv(y4, 0, 1, eng.e_final, X, X.ctx, F)
@@ -768,7 +781,7 @@ class _EncPlan(_Plan):
         self.linear(lat, self.flat_view(T5, D), D, eng.q_in, xproj, self.flat_view(T5, 2 * cd), 2 * cd)
         self.add(lambda: ops.rvq_encode(xproj, 2 * cd, eng.E, eng.Et, eng.enorm, codes, work, B * T5, T5, m.n_q, m.n_q_semantic,
                                         cd, m.codebook_size, time_major=self.tc))
-        self.finish_streaming([xin] + (ya if self.tc else y) + r_ + [y4, X], F)
+        self.finish_streaming([xin] + ya + r_ + [y4, X], F)
 
     def run(self, x: torch.Tensor, graphs: Optional[bool]) -> torch.Tensor:
         xin, L = self.xin, self.L
@@ -814,8 +827,9 @@ class _DecPlan(_Plan):
         Tin = F
         for i, r in enumerate(eng.ratios):
             Tout = Tin * r
-            yd.append(self.buf(0 if self.tc else m.residual_kernel_size - 1, Tout, 0, C // 2))
-            yda.append(self.buf(m.residual_kernel_size - 1, Tout, 0, C // 2) if self.tc else yd[-1])
+            own_copy = self.tc and not self.elu_in_transform(C // 2)
+            yd.append(self.buf(0 if own_copy else m.residual_kernel_size - 1, Tout, 0, C // 2))
+            yda.append(self.buf(m.residual_kernel_size - 1, Tout, 0, C // 2) if own_copy else yd[-1])
             hd_.append(self.buf(0, Tout, 0, C // 2 // m.compress))
             last = i == len(eng.ratios) - 1
             a.append(self.buf((m.last_kernel_size - 1) if last else 1, Tout, 0, C // 2))
@@ -833,17 +847,17 @@ class _DecPlan(_Plan):
         Tin = F
         for i, r in enumerate(eng.ratios):
             # ConvTranspose1d k=2r stride r as a 2-tap GEMM over [x[t-1], x[t]]: one output row = r time steps
-            self.conv(a[i], 0, 1, eng.d_tr[i], yd[i], yd[i].ctx, Tin, tr_stride=r, out2=yda[i] if self.tc else None,
+            self.conv(a[i], 0, 1, eng.d_tr[i], yd[i], yd[i].ctx, Tin, tr_stride=r, out2=yda[i] if yda[i] is not yd[i] else None,
                       out2_row0=yda[i].ctx)
             Tout = Tin * r
             w1, w2 = eng.d_res[i]
-            self.conv(yda[i], 0, 1, w1, hd_[i], 0, Tout, pre=ACT_NONE if self.tc else ACT_ELU, post=ACT_ELU, ffma=self.tc)
+            self.conv(yda[i], 0, 1, w1, hd_[i], 0, Tout, pre=ACT_ELU if yda[i] is yd[i] else ACT_NONE, post=ACT_ELU, ffma=self.tc)
             self.conv(hd_[i], 0, 1, w2, a[i + 1], a[i + 1].ctx, Tout, post=ACT_ELU, R=yd[i], r_row0=yd[i].ctx, ffma=self.tc)
             Tin = Tout
         last = a[-1]
         self.add(lambda: ops.conv1d_cout1(last.t, last.bs, last.ts, eng.d_final_w, eng.d_final_b, wav, Lout, B, Lout, last.C,
                                           m.last_kernel_size))
-        self.finish_streaming([qup, X] + a + (yda if self.tc else yd), F)
+        self.finish_streaming([qup, X] + a + yda, F)
         self.debug_bufs = {"qup": [qup], "X": [X], "a": a, "yd": yd, "yda": yda, "hd": hd_}   # scripts/diag_rows.py
 
     def run(self, codes: torch.Tensor, graphs: Optional[bool]) -> torch.Tensor:

@@ -473,10 +473,9 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 v = lds128(base ^ (uint32_t)(j << 4));
-          if (ACT) {
-            v.x = apply_act(v.x, p.pre_act); v.y = apply_act(v.y, p.pre_act);
-            v.z = apply_act(v.z, p.pre_act); v.w = apply_act(v.w, p.pre_act);
-          }
+          // pre-activation with the epilogues' ELU (ex2.approx): ELU(x) here == the ELU'd copy a producer epilogue would
+          // have stored, bit for bit, so a consumer may read the raw tensor instead of a second, activated one
+          if (ACT) v = apply_act4_tc(v, p.pre_act);
           const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
           for (int c = 0; c < 4; ++c) {

@@ -289,3 +289,24 @@ def test_fused_rope_attention_streaming_equals_separate_launches(official_weight
         res.append((torch.cat(cs, -1), torch.cat(ws, -1)))
     assert torch.equal(res[0][0], res[1][0])
     assert torch.equal(res[0][1], res[1][1])
+
+
+def test_elu_in_transform_equals_elu_copy(official_weights):
+    """MimiCodec.elu_in_transform_max_channels (default 0): the resblock conv reading the raw tensor and applying ELU in the
+    GEMM's operand transform gives bit-identical codes and PCM to the default (ELU'd copy written by the producer)."""
+    x = S.synthetic_audio(3, 1920 * 4, seed=78).to(DEV)
+    res = []
+    for ch in (128, 0):
+        m = MimiCodec(encoder_rates=[8, 6, 5, 4], codebook_size=2048, codebook_dim=256, rvq_layers=8)
+        m.load_state_dict(official_weights, strict=True)
+        m = m.to(DEV).eval()
+        m.elu_in_transform_max_channels = ch
+        cs, ws = [], []
+        with m.streaming(3):
+            for i in range(4):
+                c = m.encode(x[..., i * 1920:(i + 1) * 1920])
+                cs.append(c)
+                ws.append(m.decode(c))
+        res.append((torch.cat(cs, -1), torch.cat(ws, -1)))
+    assert torch.equal(res[0][0], res[1][0])
+    assert torch.equal(res[0][1], res[1][1])
