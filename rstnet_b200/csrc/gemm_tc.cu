@@ -804,6 +804,9 @@ extern "C" int rstnet_tc_gemm_create(const rstnet_tc_gemm_desc* d, rstnet_tc_pla
     const long long mt = (long long)i_tiles * d->O_out;
     const long long t64 = mt * ceil_div(N, 64), t32 = mt * ceil_div(N, 32);
     if (pl->bn == 64 && ((t32 + 147) / 148) * 2 <= ((t64 + 147) / 148) * 3) pl->bn = 32;
+    static const int force_bn = []() { const char* e = getenv("RSTNET_TC_BN"); return e ? atoi(e) : 0; }();   // tuning aid
+    if (force_bn == 64 && N >= 64) pl->bn = 64;
+    if (force_bn == 32) pl->bn = 32;
   }
   pl->prec = d->precision;
   {
