@@ -388,13 +388,42 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       n0 = nt * BN; ci = (mt % p.i_tiles) * TC_BM; co = (mt / p.i_tiles) * p.o_mul; kc = 0;
       const bool first_tile = ti == tr_ti;
       if (leader) {
-        for (int kit = 0; kit < total_k; ++kit) {
+        // Two stages per trip, the independent steps of both grouped (slot waits, then transaction counts, then the four
+        // loads): this thread shares its scheduler with four ALU-heavy warps and loses its issue slot at every dependent
+        // stall, so fewer, longer independent runs set the pace (stamps: ~350 clk per stage one stage at a time).
+        int kit = 0;
+        for (; kit + 1 < total_k; kit += 2) {
+          const int s0 = s;
+          const uint32_t ph0 = sph;
+          int s1 = s + 1;
+          uint32_t ph1 = sph;
+          if (s1 == S) { s1 = 0; ph1 ^= 1u; }
+          const int kc0 = kc, ci0 = ci, co0 = co;
+          if (++kc == p.kchunks) { kc = 0; ci += p.tap_di; co += p.tap_do; }
+          const int kc1 = kc, ci1 = ci, co1 = co;
+          if (++kc == p.kchunks) { kc = 0; ci += p.tap_di; co += p.tap_do; }
+          mbar_wait(&empty[s0], ph0 ^ 1u);
+          mbar_wait(&empty[s1], ph1 ^ 1u);
+          if (tr && first_tile) { const long long c = clock64(); p.trace[kit * 8 + 0] = c; p.trace[(kit + 1) * 8 + 0] = c; }
+          uint8_t* st0 = smem + s0 * Cfg::STAGE_BYTES;
+          uint8_t* st1 = smem + s1 * Cfg::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[s0], TC_A_BYTES + 2 * Cfg::B_BYTES);
+          mbar_arrive_expect_tx(&full[s1], TC_A_BYTES + 2 * Cfg::B_BYTES);
+          tma_load_3d(st0, &tmA, &full[s0], kc0 * TC_BKE, ci0, co0);
+          tma_load_3d(st0 + TC_A_BYTES, &tmW3, &full[s0], kit * TC_BKE, n0, 0);   // tap * Kc + kc * 32 == kit * 32
+          tma_load_3d(st1, &tmA, &full[s1], kc1 * TC_BKE, ci1, co1);
+          tma_load_3d(st1 + TC_A_BYTES, &tmW3, &full[s1], (kit + 1) * TC_BKE, n0, 0);
+          s = s1 + 1;
+          sph = ph1;
+          if (s == S) { s = 0; sph ^= 1u; }
+        }
+        if (kit < total_k) {   // odd stage count: the last stage alone
           mbar_wait(&empty[s], sph ^ 1u);
           if (tr && first_tile) p.trace[kit * 8 + 0] = clock64();
           uint8_t* st = smem + s * Cfg::STAGE_BYTES;
           mbar_arrive_expect_tx(&full[s], TC_A_BYTES + 2 * Cfg::B_BYTES);
           tma_load_3d(st, &tmA, &full[s], kc * TC_BKE, ci, co);
-          tma_load_3d(st + TC_A_BYTES, &tmW3, &full[s], kit * TC_BKE, n0, 0);   // tap * Kc + kc * 32 == kit * 32
+          tma_load_3d(st + TC_A_BYTES, &tmW3, &full[s], kit * TC_BKE, n0, 0);
           if (++kc == p.kchunks) { kc = 0; ci += p.tap_di; co += p.tap_do; }
           if (++s == S) { s = 0; sph ^= 1u; }
         }
