@@ -48,6 +48,7 @@ struct TcParams {
   int pre_act, post_act, i_tiles;
   int tma_store, c_tr;   // .ts kernel: epilogue through TMA tile stores (no residual); c_tr = output rows per o for n_split
   int m_tiles, n_tiles;  // (I tiles x O_out) and N tiles: the persistent .ts kernel walks m_tiles * n_tiles
+  int ksplit;            // .ts kernel: K slices per tile = CTAs per cluster (1, or 2 for the few-tile long-K linears)
   long long* trace;  // optional [total_k][8] clock64 stamps of CTA 0 (debug / profiling)
   long long* cta_times;  // optional [grid.x][4] %globaltimer: entry, setup done, mainloop+epilogue done, exit (blockIdx.y == 0)
 };
@@ -351,10 +352,19 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (timed) p.cta_times[blockIdx.x * 4 + 0] = gtime();
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   // A tile's K loop = taps * kchunks stages of 32 elements, in chunks of up to 4 stages (one accumulator promotion each).
-  const int total_k = p.taps * p.kchunks;
+  // K split over a 2-CTA cluster (ksplit == 2; linears whose tile count leaves half the SMs idle: a CTA's long K loop is
+  // bound by the ~58 B/clk its SM ingests from L2, two SMs ingest twice that): rank r runs stages [r, r + 1) * total_k of
+  // the tile, rank 1 hands its promoted fp32 accumulators to rank 0 through distributed shared memory, rank 0 adds them
+  // (rank order: deterministic) and runs the epilogue.  One tile per cluster.
+  const int ks = p.ksplit;
+  uint32_t crank = 0;
+  if (ks > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const int cid = (int)blockIdx.x / ks, ncl = (int)gridDim.x / ks;   // tile walker: cluster index / count
+  const int total_k = p.taps * p.kchunks / ks;
+  const int koff = (int)crank * total_k;
   const int nchunks = (total_k + CH - 1) / CH;
   const int total_tiles = p.m_tiles * p.n_tiles;
-  const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int my_tiles = (cid < total_tiles) ? (total_tiles - cid + ncl - 1) / ncl : 0;
   const int tr_ti = my_tiles > 3 ? 3 : 0;   // the traced tile: steady state when the CTA has several
 
   if (warp == 0 && lane == 0) {
@@ -383,9 +393,9 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t sph = 0;     // (g / S) & 1
     const bool leader = elect_one();   // ONE election: the running counters live in this lane's registers
     for (int ti = 0; ti < my_tiles; ++ti) {
-      const int t = blockIdx.x + ti * gridDim.x;
+      const int t = cid + ti * ncl;
       const int nt = t % p.n_tiles, mt = t / p.n_tiles;
-      n0 = nt * BN; ci = (mt % p.i_tiles) * TC_BM; co = (mt / p.i_tiles) * p.o_mul; kc = 0;
+      n0 = nt * BN; ci = (mt % p.i_tiles) * TC_BM; co = (mt / p.i_tiles) * p.o_mul; kc = koff;   // koff != 0 only with taps == 1
       const bool first_tile = ti == tr_ti;
       if (leader) {
         // Two stages per trip, the independent steps of both grouped (slot waits, then transaction counts, then the four
@@ -410,9 +420,9 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_arrive_expect_tx(&full[s0], TC_A_BYTES + 2 * Cfg::B_BYTES);
           mbar_arrive_expect_tx(&full[s1], TC_A_BYTES + 2 * Cfg::B_BYTES);
           tma_load_3d(st0, &tmA, &full[s0], kc0 * TC_BKE, ci0, co0);
-          tma_load_3d(st0 + TC_A_BYTES, &tmW3, &full[s0], kit * TC_BKE, n0, 0);   // tap * Kc + kc * 32 == kit * 32
+          tma_load_3d(st0 + TC_A_BYTES, &tmW3, &full[s0], (koff + kit) * TC_BKE, n0, 0);   // tap * Kc + kc * 32 == kit * 32
           tma_load_3d(st1, &tmA, &full[s1], kc1 * TC_BKE, ci1, co1);
-          tma_load_3d(st1 + TC_A_BYTES, &tmW3, &full[s1], (kit + 1) * TC_BKE, n0, 0);
+          tma_load_3d(st1 + TC_A_BYTES, &tmW3, &full[s1], (koff + kit + 1) * TC_BKE, n0, 0);
           s = s1 + 1;
           sph = ph1;
           if (s == S) { s = 0; sph ^= 1u; }
@@ -423,7 +433,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           uint8_t* st = smem + s * Cfg::STAGE_BYTES;
           mbar_arrive_expect_tx(&full[s], TC_A_BYTES + 2 * Cfg::B_BYTES);
           tma_load_3d(st, &tmA, &full[s], kc * TC_BKE, ci, co);
-          tma_load_3d(st + TC_A_BYTES, &tmW3, &full[s], kit * TC_BKE, n0, 0);
+          tma_load_3d(st + TC_A_BYTES, &tmW3, &full[s], (koff + kit) * TC_BKE, n0, 0);
           if (++kc == p.kchunks) { kc = 0; ci += p.tap_di; co += p.tap_do; }
           if (++s == S) { s = 0; sph ^= 1u; }
         }
@@ -531,7 +541,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int cbeg = ((warp - 10) / 4) * CW; // this warp's column range [cbeg, cbeg + CW) of the tile
     int cc = 0;
     for (int ti = 0; ti < my_tiles; ++ti) {
-      const int t = blockIdx.x + ti * gridDim.x;
+      const int t = cid + ti * ncl;
       const int nt = t % p.n_tiles, mt = t / p.n_tiles;
       const int i0 = (mt % p.i_tiles) * TC_BM, ot = mt / p.i_tiles, n0 = nt * BN;
       // bias | scale of the tile's columns -> smem (double buffered); with a single N tile they are the same for every tile
@@ -547,7 +557,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // boxes a store is still reading corrupted the tail rows of a tile -- seen rarely, on cold GPUs, on the 64->128 1x1
       // conv of the 6 kHz decoder level, scripts/diag_rows.py -- hence the read-out wait in front of every request.)
       auto request_residual = [&](int tix) {
-        const int t2 = blockIdx.x + tix * gridDim.x;
+        const int t2 = cid + tix * ncl;
         const int nt2 = t2 % p.n_tiles, mt2 = t2 / p.n_tiles;
         const int i2 = (mt2 % p.i_tiles) * TC_BM, ot2 = mt2 / p.i_tiles, n2 = nt2 * BN;
         uint8_t* boxes = reinterpret_cast<uint8_t*>(out_stage) + (tix & 1) * Cfg::BOXSET_BYTES;
@@ -563,7 +573,7 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
       };
-      if (p.tma_store && p.R) {
+      if (p.tma_store && p.R && crank == 0) {
         if (dt == 0 && ti == 0) request_residual(0);
         // The NEXT tile's residual is requested at the top of this tile, by the owner of the other box set, as soon as its
         // store of tile ti-1 has been read out: the residual is the block input, long evicted from L2, and takes ~3 000 clk
@@ -595,6 +605,28 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         tc_fence_before();
         mbar_arrive(&acc_empty[buf]);
         if (tr && ti == tr_ti && threadIdx.x == 320) p.trace[chunk * 8 + 6] = clock64();
+      }
+      if (ks > 1) {
+        // exchange buffer = box set 1 of rank 0 (unused: one tile per cluster), [BN / 4][128 rows] float4
+        const uint32_t xbuf = smem_u32(reinterpret_cast<uint8_t*>(out_stage) + Cfg::BOXSET_BYTES);
+        if (crank == 1) {
+          uint32_t rbuf;
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbuf) : "r"(xbuf), "r"(0));
+#pragma unroll
+          for (int lc = 0; lc < CW; lc += 4) {
+            const uint32_t a = rbuf + (uint32_t)((((cbeg + lc) >> 2) * TC_BM + row) * 16);
+            asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(acc[lc]), "f"(acc[lc + 1]), "f"(acc[lc + 2]),
+                         "f"(acc[lc + 3]) : "memory");
+          }
+        }
+        asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+        if (crank == 1) break;          // rank 0 finishes the tile
+#pragma unroll
+        for (int lc = 0; lc < CW; lc += 4) {
+          const float4 o = lds128(xbuf + (uint32_t)((((cbeg + lc) >> 2) * TC_BM + row) * 16));
+          acc[lc] += o.x; acc[lc + 1] += o.y; acc[lc + 2] += o.z; acc[lc + 3] += o.w;
+        }
       }
       const bool etr = tr && ti == tr_ti && threadIdx.x == 320;
       if (etr) p.trace[1 * 8 + 7] = clock64();
@@ -752,6 +784,10 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }  // DW == 4
     }
   }
+  if (ks > 1 && warp < 10) {   // the producer / MMA / transform warps' side of the hand-over barrier (all threads of both CTAs)
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+  }
   if (threadIdx.x == 320 || threadIdx.x == 352) bulk_wait0();   // the issuing threads' TMA stores are complete before the CTA (and its smem) goes away
   if (timed) p.cta_times[blockIdx.x * 4 + 2] = gtime();
   tc_fence_before();
@@ -794,7 +830,23 @@ static int tc_launch_ts(const rstnet_tc_plan* pl, cudaStream_t st) {
   using Cfg = TsCfg<BN>;
   static unsigned long long attr = 0;
   smem_optin(gemm_tc_ts_kernel<BN, DW>, Cfg::SMEM_BYTES, attr);
-  gemm_tc_ts_kernel<BN, DW><<<pl->grid_ts, 320 + 32 * DW, Cfg::SMEM_BYTES, st>>>(pl->tmA, pl->tmW3, pl->tmC, pl->tmC2, pl->tmR, pl->p);
+  if (pl->p.ksplit > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = pl->grid_ts;
+    cfg.blockDim = dim3(320 + 32 * DW);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)pl->p.ksplit;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, gemm_tc_ts_kernel<BN, DW>, pl->tmA, pl->tmW3, pl->tmC, pl->tmC2, pl->tmR, pl->p);
+  } else {
+    gemm_tc_ts_kernel<BN, DW><<<pl->grid_ts, 320 + 32 * DW, Cfg::SMEM_BYTES, st>>>(pl->tmA, pl->tmW3, pl->tmC, pl->tmC2, pl->tmR, pl->p);
+  }
   count_launch();
   return check_launch("gemm_tc_ts");
 }
@@ -926,6 +978,15 @@ extern "C" int rstnet_tc_gemm_create(const rstnet_tc_gemm_desc* d, rstnet_tc_pla
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
     const long long tiles = (long long)p.m_tiles * p.n_tiles;
     pl->grid_ts = dim3((unsigned)(tiles < sms ? tiles : sms));
+    // K split over 2-CTA clusters: plain linears (one tap) with a TMA-store epilogue, a single output, an even stage count
+    // of >= 8 per half... and few enough tiles that both halves get an SM of their own (RSTNET_TC_KSPLIT=0 turns it off)
+    static const bool ksplit_on = []() { const char* e = getenv("RSTNET_TC_KSPLIT"); return !(e && e[0] == '0'); }();
+    p.ksplit = 1;
+    if (ksplit_on && pl->ts_ok && p.tma_store && d->precision == 0 && p.taps == 1 && !p.C2 && p.n_split == 0 && p.kchunks % 2 == 0 &&
+        p.kchunks >= 16 && 2 * tiles <= sms) {
+      p.ksplit = 2;
+      pl->grid_ts = dim3((unsigned)(2 * tiles));
+    }
   }
   *out = pl;
   return 0;
