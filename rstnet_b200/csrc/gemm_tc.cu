@@ -384,6 +384,10 @@ gemm_tc_ts_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t a_tmem0 = tmem_base + (uint32_t)Cfg::ACC_COLS;
+  if (ks > 1) {   // distributed shared memory may only be written once the peer CTA is known to have started
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+  }
   if (timed) p.cta_times[blockIdx.x * 4 + 1] = gtime();
 
   if (warp == 0) {
